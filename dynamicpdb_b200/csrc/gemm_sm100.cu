@@ -1,0 +1,411 @@
+// Split-precision (bf16 x 3) tensor-core GEMM / implicit 5x5 convolution for sm_100a.
+//
+//   C[m, n] = act(alpha * sum_{tap, k} A[m + off(tap), k] * B[tap][n][k] + bias[n]) + beta * R[m, n]
+//
+// fp32 operands are pre-split by `dfold_split2d` / `dfold_conv_weight_prep` into bf16 planes
+// x = hi + lo (hi = bf16(x), lo = bf16(x - hi)); the kernel accumulates hi*hi + hi*lo + lo*hi in fp32 in
+// TMEM, which keeps ~16 mantissa bits per operand (relative error ~2^-17 per product, vs 2^-11 for plain
+// TF32/BF16 — SURVEY.md §0 "precision trap").
+//
+// Structure (one CTA = one 128 x BN output tile, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor.3d (128B swizzle) of the A / B hi+lo tiles into a
+//               multi-stage smem ring; the 3-D tensor map of the activations makes the 5x5 halo an
+//               out-of-bounds zero fill, so the convolution needs no im2col and no padding buffer.
+//   warp 1      tcgen05.mma issuer (one elected lane): 3 products x 4 K-steps of UMMA 128xBNx16 per stage,
+//               accumulator in TMEM; tcgen05.commit releases the smem stage / signals the epilogue.
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns, bias / activation / residual, fp32 stores.
+//
+// Replaces (reference file:line): nn.Linear in src/model/ipa_pytorch_dynamic.py:284-305,757-796,590,
+// openfold/model/structure_module.py:102-110,58-59; nn.Conv2d stack src/model/ipa_pytorch_dynamic.py:664-706.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace dfold {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 192;
+
+template <int BN> struct TileCfg {
+    static constexpr int kStages = (BN >= 256) ? 2 : ((BN >= 128) ? 3 : 4);
+    static constexpr int kABytes = BM * BK * 2;               // one plane
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kTmemCols = (BN <= 32) ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+};
+
+struct GemmParams {
+    int mode;            // 0: A rows = (frame, residue) tiles, taps outer / K inner   1: wgrad (K = pixels)
+    int num_kb;          // k-blocks per tile
+    int kc;              // mode 0: k-chunks per tap; mode 1: residue blocks per frame
+    int taps_n, taps_f;  // tap grid (1x1 for a plain linear)
+    int tiles_per_frame; // mode 0: ceil(Nr / 128)
+    int Nr;              // mode 0: residues per frame (rows per frame)
+    long out_rows;       // valid rows of the output (mode 0: F*Nr, mode 1: M)
+    int n_out;           // valid columns
+    float* out; long ldo; long out_tap_stride;
+    const float* bias;
+    const float* res; long ldr;
+    float alpha, beta;
+    int act;             // 0 none, 1 relu, 2 silu
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address  [0,14)
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset   [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                   const GemmParams p) {
+    using Cfg = TileCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;   // 8-byte aligned
+    // barrier layout: full[kStages], empty[kStages], tmem_full, then the tmem pointer word
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::kStages);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- tile coordinates ----
+    const int n_tile = blockIdx.x;                 // output column tile
+    const int m_tile = blockIdx.y;
+    const int tap_z = blockIdx.z;                  // mode 1 only
+    int f0 = 0, n0 = 0, m0 = 0;
+    if (p.mode == 0) {
+        f0 = m_tile / p.tiles_per_frame;
+        n0 = (m_tile % p.tiles_per_frame) * BM;
+    } else {
+        m0 = m_tile * BM;
+    }
+    const int col0 = n_tile * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % Cfg::kStages;
+                const uint32_t ph = (kb / Cfg::kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+                const uint32_t sa_hi = smem_base + s * Cfg::kStageBytes;
+                const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                const uint32_t sb_hi = sa_lo + Cfg::kABytes;
+                const uint32_t sb_lo = sb_hi + Cfg::kBBytes;
+                if (p.mode == 0) {
+                    const int tap = kb / p.kc, c = kb % p.kc;
+                    const int dn = tap % p.taps_n - p.taps_n / 2;
+                    const int df = tap / p.taps_n - p.taps_f / 2;
+                    tma_load_3d(sa_hi, &map_a_hi, full_bar(s), c * BK, n0 + dn, f0 + df);
+                    tma_load_3d(sa_lo, &map_a_lo, full_bar(s), c * BK, n0 + dn, f0 + df);
+                    tma_load_3d(sb_hi, &map_b_hi, full_bar(s), c * BK, col0, tap);
+                    tma_load_3d(sb_lo, &map_b_lo, full_bar(s), c * BK, col0, tap);
+                } else {
+                    const int f = kb / p.kc, j = kb % p.kc;
+                    const int dn = tap_z % p.taps_n - p.taps_n / 2;
+                    const int df = tap_z / p.taps_n - p.taps_f / 2;
+                    tma_load_3d(sa_hi, &map_a_hi, full_bar(s), j * BK, f, m0);
+                    tma_load_3d(sa_lo, &map_a_lo, full_bar(s), j * BK, f, m0);
+                    tma_load_3d(sb_hi, &map_b_hi, full_bar(s), j * BK + dn, f + df, col0);
+                    tma_load_3d(sb_lo, &map_b_lo, full_bar(s), j * BK + dn, f + df, col0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % Cfg::kStages;
+                const uint32_t ph = (kb / Cfg::kStages) & 1;
+                mbar_wait(full_bar(s), ph);
+                tcgen05_fence_after();
+                const uint32_t sa_hi = smem_base + s * Cfg::kStageBytes;
+                const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                const uint32_t sb_hi = sa_lo + Cfg::kABytes;
+                const uint32_t sb_lo = sb_hi + Cfg::kBBytes;
+                const uint64_t da_hi = make_sw128_desc(sa_hi), da_lo = make_sw128_desc(sa_lo);
+                const uint64_t db_hi = make_sw128_desc(sb_hi), db_lo = make_sw128_desc(sb_lo);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step, in 16 B units
+                    umma_bf16(tmem_base, da_lo + koff, db_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem_base, da_hi + koff, db_lo + koff, idesc, 1u);
+                    umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, 1u);
+                }
+                umma_commit(empty_bar(s));      // smem stage reusable once these MMAs retire
+            }
+            umma_commit(tmem_full_bar);         // accumulator complete
+        }
+    } else {
+        // =============================== epilogue (warps 2..5) ===============================
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;                    // row inside the tile
+        long grow;                                      // global output row
+        bool row_ok;
+        if (p.mode == 0) {
+            const int n = n0 + r;
+            row_ok = (n < p.Nr) && ((long)f0 * p.Nr + n < p.out_rows);
+            grow = (long)f0 * p.Nr + n;
+        } else {
+            grow = m0 + r;
+            row_ok = grow < p.out_rows;
+        }
+        float* orow = p.out + (p.mode == 1 ? (long)tap_z * p.out_tap_stride : 0) + grow * p.ldo;
+        const float* rrow = p.res ? p.res + grow * p.ldr : nullptr;
+        const bool vec_ok = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                            (p.out_tap_stride % 4 == 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!row_ok) continue;
+            const int gc0 = col0 + c0;
+            if (gc0 >= p.n_out) continue;
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float x = __uint_as_float(v[i]) * p.alpha;
+                const int gc = gc0 + i;
+                if (gc < p.n_out) {
+                    if (p.bias) x += __ldg(p.bias + gc);
+                    if (p.act == 1) x = fmaxf(x, 0.f);
+                    else if (p.act == 2) x = x / (1.f + __expf(-x));
+                    if (rrow) x += p.beta * __ldg(rrow + gc);
+                }
+                o[i] = x;
+            }
+            if (vec_ok && gc0 + 32 <= p.n_out) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(orow + gc0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (gc0 + i < p.n_out) orow[gc0 + i] = o[i];
+            }
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// bf16 tensor with dims d0 (innermost, contiguous), d1, d2; strides in ELEMENTS for d1, d2.
+int make_map(CUtensorMap* m, const void* base, long d0, long d1, long d2, long s1, long s2, int b0, int b1, int b2) {
+    EncodeTiledFn enc = get_encode();
+    DFOLD_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+    DFOLD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+    DFOLD_REQUIRE((s1 * 2) % 16 == 0 && (s2 * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes (s1=%ld s2=%ld)", s1, s2);
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
+    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DFOLD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) dims=(%ld,%ld,%ld) strides=(%ld,%ld) box=(%d,%d,%d)",
+                  (int)r, d0, d1, d2, s1, s2, b0, b1, b2);
+    return 0;
+}
+
+template <int BN>
+int launch(const CUtensorMap* maps, const GemmParams& p, dim3 grid, cudaStream_t st) {
+    using Cfg = TileCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        DFOLD_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+        configured = true;
+    }
+    gemm_bf16x3_kernel<BN><<<grid, NTHREADS, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    return check_launch("gemm_bf16x3_kernel");
+}
+
+int pick_bn(long n_out) {
+    if (n_out % 256 == 0 || n_out > 640) return 256;
+    if (n_out > 64) return 128;
+    return 64;
+}
+
+}  // namespace
+}  // namespace dfold
+
+using namespace dfold;
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dfold_gemm_bf16x3(
+    const uint16_t* a_hi, const uint16_t* a_lo, long F, long Nr, long K, long lda,
+    const uint16_t* b_hi, const uint16_t* b_lo, long n_out, long ldb, int taps_f, int taps_n,
+    float* out, long ldo, const float* bias, const float* residual, long ldr,
+    float alpha, float beta, int act, void* stream) {
+    DFOLD_REQUIRE(F > 0 && Nr > 0 && K > 0 && n_out > 0, "dfold_gemm_bf16x3: empty problem");
+    DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dfold_gemm_bf16x3: lda/ldb must be multiples of 8 (got %ld, %ld)", lda, ldb);
+    DFOLD_REQUIRE(taps_f >= 1 && taps_n >= 1 && (taps_f & 1) && (taps_n & 1), "dfold_gemm_bf16x3: tap grid must be odd");
+    const int bn = pick_bn(n_out);
+    CUtensorMap maps[4];
+    // A: dims (K, Nr, F)   B: dims (K, n_out, taps)
+    if (make_map(&maps[0], a_hi, K, Nr, F, lda, Nr * lda, BK, BM, 1)) return 1;
+    if (make_map(&maps[1], a_lo, K, Nr, F, lda, Nr * lda, BK, BM, 1)) return 1;
+    const long taps = (long)taps_f * taps_n;
+    if (make_map(&maps[2], b_hi, K, n_out, taps, ldb, n_out * ldb, BK, bn, 1)) return 1;
+    if (make_map(&maps[3], b_lo, K, n_out, taps, ldb, n_out * ldb, BK, bn, 1)) return 1;
+    GemmParams p{};
+    p.mode = 0;
+    p.kc = (int)cdiv(K, BK);
+    p.num_kb = (int)(taps * p.kc);
+    p.taps_n = taps_n; p.taps_f = taps_f;
+    p.tiles_per_frame = (int)cdiv(Nr, BM);
+    p.Nr = (int)Nr;
+    p.out_rows = F * Nr;
+    p.n_out = (int)n_out;
+    p.out = out; p.ldo = ldo; p.out_tap_stride = 0;
+    p.bias = bias; p.res = residual; p.ldr = ldr;
+    p.alpha = alpha; p.beta = beta; p.act = act;
+    dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(F * p.tiles_per_frame), 1);
+    cudaStream_t st = as_stream(stream);
+    if (bn == 256) return launch<256>(maps, p, grid, st);
+    if (bn == 128) return launch<128>(maps, p, grid, st);
+    return launch<64>(maps, p, grid, st);
+}
+
+// out[tap][m][n] = sum_{f, j} At[m][f][j] * Bt[n][f + df(tap)][j + dn(tap)]      (weight gradient; K = pixels)
+extern "C" int dfold_gemm_wgrad_bf16x3(
+    const uint16_t* at_hi, const uint16_t* at_lo, long M,
+    const uint16_t* bt_hi, const uint16_t* bt_lo, long Nn,
+    long F, long Nr, long ldp, int taps_f, int taps_n,
+    float* out, long ldo, float alpha, void* stream) {
+    DFOLD_REQUIRE(M > 0 && Nn > 0 && F > 0 && Nr > 0, "dfold_gemm_wgrad_bf16x3: empty problem");
+    DFOLD_REQUIRE(ldp % 8 == 0, "dfold_gemm_wgrad_bf16x3: ldp must be a multiple of 8 (got %ld)", ldp);
+    const int bn = pick_bn(Nn);
+    CUtensorMap maps[4];
+    // planes are [rows][F][ldp]; dims (Nr, F, rows)
+    if (make_map(&maps[0], at_hi, Nr, F, M, ldp, F * ldp, BK, 1, BM)) return 1;
+    if (make_map(&maps[1], at_lo, Nr, F, M, ldp, F * ldp, BK, 1, BM)) return 1;
+    if (make_map(&maps[2], bt_hi, Nr, F, Nn, ldp, F * ldp, BK, 1, bn)) return 1;
+    if (make_map(&maps[3], bt_lo, Nr, F, Nn, ldp, F * ldp, BK, 1, bn)) return 1;
+    GemmParams p{};
+    p.mode = 1;
+    p.kc = (int)cdiv(Nr, BK);
+    p.num_kb = (int)(F * p.kc);
+    p.taps_n = taps_n; p.taps_f = taps_f;
+    p.tiles_per_frame = 1; p.Nr = (int)Nr;
+    p.out_rows = M; p.n_out = (int)Nn;
+    p.out = out; p.ldo = ldo; p.out_tap_stride = M * ldo;
+    p.bias = nullptr; p.res = nullptr; p.ldr = 0;
+    p.alpha = alpha; p.beta = 0.f; p.act = 0;
+    dim3 grid((unsigned)cdiv(Nn, bn), (unsigned)cdiv(M, BM), (unsigned)(taps_f * taps_n));
+    cudaStream_t st = as_stream(stream);
+    if (bn == 256) return launch<256>(maps, p, grid, st);
+    if (bn == 128) return launch<128>(maps, p, grid, st);
+    return launch<64>(maps, p, grid, st);
+}

@@ -1,0 +1,685 @@
+"""Autograd-aware operator surface over the C-ABI library ``libdfold_b200.so`` (include/dfold_b200.h).
+
+Every function here launches hand-written sm_100a kernels through ctypes with raw device pointers and the
+current CUDA stream.  There is NO CPU path and no fallback to torch library kernels for the arithmetic: if the
+shared library is missing, or a tensor is not on a CUDA device, the ops raise.  (The tests exercise the host-side
+module logic on CPU by monkey-patching these names with the oracle — that seam lives in tests/, not here.)
+
+torch is used for: device memory (``torch.empty``), streams, autograd bookkeeping, and trivial view / elementwise
+glue (cat, slicing, SiLU on tiny tensors, masks).
+"""
+import ctypes
+import os
+import weakref
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdfold_b200.so")
+_LIB = None
+
+# signature mini-language: p pointer, l long, i int, f float
+_SIGS = {
+    "dfold_abi_version": "",
+    "dfold_split2d": "plllipl" + "ppll" + "ppll" + "pp",
+    "dfold_conv_weight_prep": "piii" + "ppl" + "ppl" + "p",
+    "dfold_taps_to_param": "piiipp",
+    "dfold_sgemm": "pllll" * 4 + "p" + "iiiii" + "ff" + "ii" + "p",
+    "dfold_global_layernorm_fwd": "pppplfip",
+    "dfold_global_layernorm_bwd": "pppppl" + "ip",
+    "dfold_row_layernorm_fwd": "ppppplifp",
+    "dfold_row_layernorm_bwd": "ppppppplip",
+    "dfold_quat_to_rot_fwd": "pplp",
+    "dfold_quat_to_rot_bwd": "ppplp",
+    "dfold_rigid_apply_fwd": "ppplp" + "lliip",
+    "dfold_rigid_apply_bwd": "ppplp" + "ppp" + "lliip",
+    "dfold_compose_q_update_fwd": "pppppplp",
+    "dfold_compose_q_update_bwd": "pppppppplp",
+    "dfold_gemm_bf16x3": "ppllll" + "ppllii" + "pl" + "p" + "pl" + "ffi" + "p",
+    "dfold_gemm_wgrad_bf16x3": "ppl" + "ppl" + "lllii" + "plf" + "p",
+    "dfold_ipa_attn_fwd": "plplppplpppp" + "iiiiiiii" + "ff" + "ppp",
+    "dfold_ipa_attn_bwd": "plplppplpppp" + "iiiiiiii" + "ff" + "ppp" + "ppppppppp" + "p",
+}
+_CT = {"p": ctypes.c_void_p, "l": ctypes.c_long, "i": ctypes.c_int, "f": ctypes.c_float}
+
+
+def lib():
+    """Load the C-ABI library (fails loudly when it has not been built)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build the sm_100a extension first (python -m dynamicpdb_b200.build or "
+                "__graft_entry__.build()).  dynamicpdb_b200 has no CPU / PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, sig in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = [_CT[c] for c in sig]
+            fn.restype = ctypes.c_int
+        L.dfold_last_error.restype = ctypes.c_char_p
+        L.dfold_last_error.argtypes = []
+        _LIB = L
+    return _LIB
+
+
+def exported_symbols():
+    return sorted(list(_SIGS) + ["dfold_last_error"])
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what}: {lib().dfold_last_error().decode()}")
+
+
+def _ptr(t: Optional[torch.Tensor], offset: int = 0):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr() + offset * t.element_size())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dynamicpdb_b200 ops need CUDA tensors (B200 / sm_100a); there is no CPU fallback")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+# --------------------------------------------------------------------------------------------------
+# raw launch helpers
+# --------------------------------------------------------------------------------------------------
+def _sgemm(A, a_off, a_rs, a_cs, a_bs, a_bs2, B, b_off, b_rs, b_cs, b_bs, b_bs2, C, c_off, c_rs, c_cs, c_bs, c_bs2,
+           M, N, K, *, R=None, r_off=0, r_rs=0, r_cs=0, r_bs=0, r_bs2=0, bias=None, batch=1, batch2=1,
+           alpha=1.0, beta=1.0, act=0, pre_relu=0):
+    _check(lib().dfold_sgemm(_ptr(A, a_off), a_rs, a_cs, a_bs, a_bs2, _ptr(B, b_off), b_rs, b_cs, b_bs, b_bs2,
+                             _ptr(C, c_off), c_rs, c_cs, c_bs, c_bs2, _ptr(R, r_off), r_rs, r_cs, r_bs, r_bs2,
+                             _ptr(bias), batch, batch2, M, N, K, alpha, beta, act, pre_relu, _stream()), "dfold_sgemm")
+
+
+def _split2d(x2: torch.Tensor, *, pre_relu=False, gate=None, want=True, want_t=False, colsum=None,
+             t_out=None, t_ld=None, t_off=0, rpad=None):
+    """x2 [R, C] fp32 contiguous -> (hi, lo) [R, C8] and / or transposed planes [C, R8] (or into ``t_out``)."""
+    R, C = x2.shape
+    hi = lo = hit = lot = None
+    c8 = _pad8(C)
+    if want:
+        hi = torch.empty((R, c8), dtype=torch.int16, device=x2.device)
+        lo = torch.empty((R, c8), dtype=torch.int16, device=x2.device)
+    ldt = 0
+    rp = 0
+    if want_t:
+        if t_out is None:
+            r8 = _pad8(R)
+            hit = torch.empty((C, r8), dtype=torch.int16, device=x2.device)
+            lot = torch.empty((C, r8), dtype=torch.int16, device=x2.device)
+            ldt, rp = r8, r8
+        else:
+            hit, lot = t_out
+            ldt, rp = t_ld, rpad
+    _check(lib().dfold_split2d(_ptr(x2), R, C, x2.stride(0), int(pre_relu), _ptr(gate), gate.stride(0) if gate is not None else 0,
+                               _ptr(hi), _ptr(lo), c8, c8, _ptr(hit, t_off), _ptr(lot, t_off), ldt, rp,
+                               _ptr(colsum), _stream()), "dfold_split2d")
+    return (hi, lo), (hit, lot)
+
+
+_WCACHE = {}
+
+
+def _cache_get(kind, w: torch.Tensor, build):
+    """bf16 operand planes of a weight, rebuilt whenever the tensor object or its version counter changes
+    (optimizer steps and load_state_dict bump ``_version``)."""
+    key = (kind, id(w))
+    ent = _WCACHE.get(key)
+    if ent is not None and ent[0]() is w and ent[1] == (w._version, w.data_ptr()):
+        return ent[2]
+    val = build()
+    if len(_WCACHE) > 512:
+        for k in [k for k, e in _WCACHE.items() if e[0]() is None]:
+            del _WCACHE[k]
+    _WCACHE[key] = (weakref.ref(w), (w._version, w.data_ptr()), val)
+    return val
+
+
+def _linear_planes(w: torch.Tensor):
+    """(hi, lo) [N, K8] and transposed (hi_t, lo_t) [K, N8] bf16 planes of a Linear weight, cached per version."""
+    def build():
+        with torch.no_grad():
+            (hi, lo), (hit, lot) = _split2d(_f32c(w.detach()), want=True, want_t=True)
+        return hi, lo, hit, lot
+    return _cache_get("lin", w, build)
+
+
+def _conv_planes(w: torch.Tensor):
+    """fwd planes [25][O][I8] and dgrad planes [25][I][O8] (tap-flipped) of a conv weight [O, I, kh, kw]."""
+    def build():
+        O, I, kh, kw = w.shape
+        T = kh * kw
+        i8, o8 = _pad8(I), _pad8(O)
+        mk = lambda *s: torch.zeros(s, dtype=torch.int16, device=w.device)
+        f_hi, f_lo, d_hi, d_lo = mk(T, O, i8), mk(T, O, i8), mk(T, I, o8), mk(T, I, o8)
+        _check(lib().dfold_conv_weight_prep(_ptr(_f32c(w.detach())), O, I, T, _ptr(f_hi), _ptr(f_lo), i8,
+                                            _ptr(d_hi), _ptr(d_lo), o8, _stream()), "dfold_conv_weight_prep")
+        return f_hi, f_lo, d_hi, d_lo
+    return _cache_get("conv", w, build)
+
+
+def _gemm(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act):
+    _check(lib().dfold_gemm_bf16x3(_ptr(a_hi), _ptr(a_lo), F, Nr, K, lda, _ptr(b_hi), _ptr(b_lo), n_out, ldb, taps_f, taps_n,
+                                   _ptr(out), ldo, _ptr(bias), _ptr(residual), ldr, alpha, beta, act, _stream()),
+           "dfold_gemm_bf16x3")
+
+
+def _gemm_wgrad(at, M, bt, Nn, F, Nr, ldp, taps_f, taps_n, out, ldo):
+    _check(lib().dfold_gemm_wgrad_bf16x3(_ptr(at[0]), _ptr(at[1]), M, _ptr(bt[0]), _ptr(bt[1]), Nn, F, Nr, ldp, taps_f, taps_n,
+                                         _ptr(out), ldo, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3")
+
+
+_ACT = {None: 0, "relu": 1}
+
+
+def _use_tensor_cores(M: int, N: int, K: int) -> bool:
+    # the 128 x BN tcgen05 tile needs 16-byte aligned K rows; tiny problems stay on the SIMT kernel
+    return K % 8 == 0 and K >= 64 and N >= 16 and M >= 32 and (M * N * K) >= (1 << 18)
+
+
+# --------------------------------------------------------------------------------------------------
+# linear
+# --------------------------------------------------------------------------------------------------
+class _LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act, residual, pre_relu):
+        _need_cuda(x, w, b, residual)
+        K_ = w.shape[1]
+        N_ = w.shape[0]
+        x2 = _f32c(x.reshape(-1, K_))
+        M_ = x2.shape[0]
+        wf = _f32c(w)
+        bf = _f32c(b) if b is not None else None
+        r2 = _f32c(residual.reshape(-1, N_)) if residual is not None else None
+        out = torch.empty((M_, N_), dtype=torch.float32, device=x.device)
+        tc = _use_tensor_cores(M_, N_, K_)
+        if tc:
+            (a_hi, a_lo), _ = _split2d(x2, pre_relu=pre_relu)
+            w_hi, w_lo, _, _ = _linear_planes(w)
+            _gemm(a_hi, a_lo, 1, M_, K_, a_hi.shape[1], w_hi, w_lo, N_, w_hi.shape[1], 1, 1, out, N_, bf, r2, N_, 1.0, 1.0, _ACT[act])
+        else:
+            _sgemm(x2, 0, K_, 1, 0, 0, wf, 0, K_, 1, 0, 0, out, 0, N_, 1, 0, 0, M_, N_, K_, R=r2, r_rs=N_, r_cs=1,
+                   bias=bf, act=_ACT[act], pre_relu=int(pre_relu))
+        ctx.save_for_backward(x2, w, out if act == "relu" else None, r2 if act == "relu" else None)
+        ctx.meta = (x.shape, act, pre_relu, tc, b is not None, residual is not None and residual.shape)
+        return out.reshape(x.shape[:-1] + (N_,))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, out, r2 = ctx.saved_tensors
+        xshape, act, pre_relu, tc, has_b, rshape = ctx.meta
+        M_, K_ = x2.shape
+        N_ = w.shape[0]
+        g = _f32c(dy.reshape(M_, N_))
+        gate = None
+        if act == "relu":
+            gate = out if r2 is None else (out - r2)
+        dres = dy.reshape(rshape) if rshape else None
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_b and ctx.needs_input_grad[2]
+        dx = dw = db = None
+        if tc:
+            db_buf = torch.zeros(N_, dtype=torch.float32, device=g.device) if need_b else None
+            (g_hi, g_lo), (gt_hi, gt_lo) = _split2d(g, gate=gate, want=need_x, want_t=need_w, colsum=db_buf)
+            db = db_buf
+            if need_x:
+                _, _, wt_hi, wt_lo = _linear_planes(w)
+                dx = torch.empty((M_, K_), dtype=torch.float32, device=g.device)
+                _gemm(g_hi, g_lo, 1, M_, N_, g_hi.shape[1], wt_hi, wt_lo, K_, wt_hi.shape[1], 1, 1, dx, K_, None, None, 0, 1.0, 0.0, 0)
+            if need_w:
+                _, (xt_hi, xt_lo) = _split2d(x2, pre_relu=pre_relu, want=False, want_t=True)
+                dw = torch.empty((N_, K_), dtype=torch.float32, device=g.device)
+                _gemm_wgrad((gt_hi, gt_lo), N_, (xt_hi, xt_lo), K_, 1, M_, gt_hi.shape[1], 1, 1, dw, K_)
+        else:
+            if gate is not None:
+                g = g * (gate > 0)
+            wf = _f32c(w)
+            if need_x:
+                dx = torch.empty((M_, K_), dtype=torch.float32, device=g.device)
+                _sgemm(g, 0, N_, 1, 0, 0, wf, 0, 1, K_, 0, 0, dx, 0, K_, 1, 0, 0, M_, K_, N_)
+            if need_w:
+                dw = torch.empty((N_, K_), dtype=torch.float32, device=g.device)
+                xr = torch.relu(x2) if pre_relu else x2
+                _sgemm(g, 0, 1, N_, 0, 0, xr, 0, 1, K_, 0, 0, dw, 0, K_, 1, 0, 0, N_, K_, M_)
+            if need_b:
+                db = g.sum(0)
+        if dx is not None:
+            if pre_relu:
+                dx = dx * (x2 > 0)
+            dx = dx.reshape(xshape)
+        return dx, dw, db, None, dres, None
+
+
+def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, pre_relu: bool = False):
+    """``act(relu?(x) @ weight.T + bias) + residual``; act in {None, 'relu', 'silu'}."""
+    if act == "silu":
+        y = torch.nn.functional.silu(_LinearFn.apply(x, weight, bias, None, None, pre_relu))
+        return y if residual is None else y + residual
+    return _LinearFn.apply(x, weight, bias, act, residual, pre_relu)
+
+
+# --------------------------------------------------------------------------------------------------
+# 5x5 (frame x residue) convolution, channels-last, implicit GEMM
+# --------------------------------------------------------------------------------------------------
+def _frame_transposed_planes(x2: torch.Tensor, F: int, N: int, gate=None, colsum=None):
+    """x2 [F*N, C] -> bf16 planes laid out [C][F][N8] (N8 = N rounded to 8) for the weight-gradient GEMM."""
+    C = x2.shape[1]
+    n8 = _pad8(N)
+    if n8 == N:
+        _, (hit, lot) = _split2d(x2, gate=gate, want=False, want_t=True, colsum=colsum)
+        return hit, lot, n8
+    hit = torch.empty((C, F, n8), dtype=torch.int16, device=x2.device)
+    lot = torch.empty((C, F, n8), dtype=torch.int16, device=x2.device)
+    for f in range(F):
+        _split2d(x2[f * N:(f + 1) * N], gate=None if gate is None else gate[f * N:(f + 1) * N], want=False, want_t=True,
+                 colsum=colsum, t_out=(hit, lot), t_ld=F * n8, t_off=f * n8, rpad=n8)
+    return hit, lot, n8
+
+
+class _Conv5x5Fn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, relu, residual):
+        _need_cuda(x, w, b, residual)
+        F_, N_, Ci = x.shape
+        Co, Ci2, kh, kw = w.shape
+        if Ci2 != Ci or Ci % 8 or Co % 8:
+            raise ValueError(f"conv5x5: channels must match and be multiples of 8 (got {Ci}->{Co})")
+        x2 = _f32c(x.reshape(F_ * N_, Ci))
+        r2 = _f32c(residual.reshape(F_ * N_, Co)) if residual is not None else None
+        out = torch.empty((F_ * N_, Co), dtype=torch.float32, device=x.device)
+        (a_hi, a_lo), _ = _split2d(x2)
+        f_hi, f_lo, _, _ = _conv_planes(w)
+        _gemm(a_hi, a_lo, F_, N_, Ci, Ci, f_hi, f_lo, Co, f_hi.shape[2], kh, kw, out, Co, _f32c(b) if b is not None else None,
+              r2, Co, 1.0, 1.0, 1 if relu else 0)
+        ctx.save_for_backward(x2, w, out if relu else None, r2 if relu else None)
+        ctx.meta = (x.shape, relu, b is not None, residual is not None)
+        return out.reshape(F_, N_, Co)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, out, r2 = ctx.saved_tensors
+        (F_, N_, Ci), relu, has_b, has_r = ctx.meta
+        Co, _, kh, kw = w.shape
+        g = _f32c(dy.reshape(F_ * N_, Co))
+        gate = None
+        if relu:
+            gate = out if r2 is None else (out - r2)
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_b and ctx.needs_input_grad[2]
+        dx = dw = db = None
+        db_buf = torch.zeros(Co, dtype=torch.float32, device=g.device) if need_b else None
+        if need_x or need_b:
+            (g_hi, g_lo), _ = _split2d(g, gate=gate, want=need_x, colsum=db_buf)
+            db = db_buf
+        if need_x:
+            _, _, d_hi, d_lo = _conv_planes(w)
+            dx = torch.empty((F_ * N_, Ci), dtype=torch.float32, device=g.device)
+            _gemm(g_hi, g_lo, F_, N_, Co, Co, d_hi, d_lo, Ci, d_hi.shape[2], kh, kw, dx, Ci, None, None, 0, 1.0, 0.0, 0)
+            dx = dx.reshape(F_, N_, Ci)
+        if need_w:
+            gt_hi, gt_lo, n8 = _frame_transposed_planes(g, F_, N_, gate=gate)
+            xt_hi, xt_lo, _ = _frame_transposed_planes(x2, F_, N_)
+            taps = torch.empty((kh * kw, Co, Ci), dtype=torch.float32, device=g.device)
+            _gemm_wgrad((gt_hi, gt_lo), Co, (xt_hi, xt_lo), Ci, F_, N_, n8, kh, kw, taps, Ci)
+            dw = torch.empty((Co, Ci, kh, kw), dtype=torch.float32, device=g.device)
+            _check(lib().dfold_taps_to_param(_ptr(taps), Co, Ci, kh * kw, _ptr(dw), _stream()), "dfold_taps_to_param")
+        return dx, dw, db, None, (dy if has_r else None)
+
+
+def conv5x5(x, weight, bias=None, relu: bool = True, residual=None):
+    """Channels-last ``Conv2d(kernel 5, padding 2)`` over the (frame, residue) image: x [F, N, C_in] ->
+    ``relu?(conv(x) + bias) + residual`` [F, N, C_out]; weight keeps the reference's [C_out, C_in, 5, 5] layout."""
+    return _Conv5x5Fn.apply(x, weight, bias, relu, residual)
+
+
+# --------------------------------------------------------------------------------------------------
+# norms
+# --------------------------------------------------------------------------------------------------
+class _GlobalLNFn(Function):
+    @staticmethod
+    def forward(ctx, x, eps, silu):
+        _need_cuda(x)
+        xc = _f32c(x)
+        y = torch.empty_like(xc)
+        stats = torch.empty(2, dtype=torch.float32, device=x.device)
+        ws = torch.empty(2048 + 2, dtype=torch.float64, device=x.device)
+        _check(lib().dfold_global_layernorm_fwd(_ptr(xc), _ptr(y), _ptr(stats), _ptr(ws), xc.numel(), eps, int(silu), _stream()),
+               "dfold_global_layernorm_fwd")
+        ctx.save_for_backward(xc, stats)
+        ctx.silu = silu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, stats = ctx.saved_tensors
+        g = _f32c(dy)
+        dx = torch.empty_like(xc)
+        ws = torch.empty(2048 + 2, dtype=torch.float64, device=xc.device)
+        _check(lib().dfold_global_layernorm_bwd(_ptr(xc), _ptr(g), _ptr(stats), _ptr(ws), _ptr(dx), xc.numel(), int(ctx.silu), _stream()),
+               "dfold_global_layernorm_bwd")
+        return dx, None, None
+
+
+def global_layernorm(x, eps: float = 1e-4, silu: bool = False):
+    """MyLayerNorm: one mean / unbiased variance over the whole tensor, optional fused SiLU."""
+    return _GlobalLNFn.apply(x, eps, silu)
+
+
+class _RowLNFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        _need_cuda(x, w, b)
+        C = x.shape[-1]
+        x2 = _f32c(x.reshape(-1, C))
+        y = torch.empty_like(x2)
+        stats = torch.empty((x2.shape[0], 2), dtype=torch.float32, device=x.device)
+        _check(lib().dfold_row_layernorm_fwd(_ptr(x2), _ptr(_f32c(w)), _ptr(_f32c(b)), _ptr(y), _ptr(stats), x2.shape[0], C, eps, _stream()),
+               "dfold_row_layernorm_fwd")
+        ctx.save_for_backward(x2, w, stats)
+        ctx.shape = x.shape
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, stats = ctx.saved_tensors
+        C = x2.shape[1]
+        g = _f32c(dy.reshape(-1, C))
+        dx = torch.empty_like(x2)
+        dw = torch.zeros(C, dtype=torch.float32, device=x2.device)
+        db = torch.zeros(C, dtype=torch.float32, device=x2.device)
+        _check(lib().dfold_row_layernorm_bwd(_ptr(x2), _ptr(_f32c(w)), _ptr(g), _ptr(stats), _ptr(dx), _ptr(dw), _ptr(db), x2.shape[0], C, _stream()),
+               "dfold_row_layernorm_bwd")
+        return dx.reshape(ctx.shape), dw, db, None
+
+
+def layer_norm(x, weight, bias, eps: float = 1e-5):
+    return _RowLNFn.apply(x, weight, bias, eps)
+
+
+# --------------------------------------------------------------------------------------------------
+# rigid algebra
+# --------------------------------------------------------------------------------------------------
+class _QuatToRotFn(Function):
+    @staticmethod
+    def forward(ctx, q):
+        _need_cuda(q)
+        qc = _f32c(q)
+        n = qc.numel() // 4
+        R = torch.empty(qc.shape[:-1] + (3, 3), dtype=torch.float32, device=q.device)
+        _check(lib().dfold_quat_to_rot_fwd(_ptr(qc), _ptr(R), n, _stream()), "dfold_quat_to_rot_fwd")
+        ctx.save_for_backward(qc)
+        return R
+
+    @staticmethod
+    def backward(ctx, dR):
+        (qc,) = ctx.saved_tensors
+        dq = torch.empty_like(qc)
+        _check(lib().dfold_quat_to_rot_bwd(_ptr(qc), _ptr(_f32c(dR)), _ptr(dq), qc.numel() // 4, _stream()), "dfold_quat_to_rot_bwd")
+        return dq
+
+
+def quat_to_rot(q):
+    if q.numel() == 0:
+        return q.new_zeros(q.shape[:-1] + (3, 3))
+    return _QuatToRotFn.apply(q)
+
+
+class _RigidApplyFn(Function):
+    """quat [F,N,4], trans [F,N,3], pts [Fp,N,m,3] with Fp in {1, F} -> [F,N,m,3]."""
+
+    @staticmethod
+    def forward(ctx, quat, trans, pts, inverse):
+        F_, N_ = quat.shape[0], quat.shape[1]
+        m = pts.shape[2]
+        out = torch.empty((F_, N_, m, 3), dtype=torch.float32, device=quat.device)
+        fs = 0 if pts.shape[0] == 1 else N_ * m * 3
+        _check(lib().dfold_rigid_apply_fwd(_ptr(quat), _ptr(trans), _ptr(pts), fs, _ptr(out), F_, N_, m, int(inverse), _stream()),
+               "dfold_rigid_apply_fwd")
+        ctx.save_for_backward(quat, trans, pts)
+        ctx.inverse = inverse
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        quat, trans, pts = ctx.saved_tensors
+        F_, N_ = quat.shape[0], quat.shape[1]
+        m = pts.shape[2]
+        fs = 0 if pts.shape[0] == 1 else N_ * m * 3
+        dpts = torch.empty((F_, N_, m, 3), dtype=torch.float32, device=quat.device)
+        dq = torch.empty_like(quat)
+        dt = torch.empty_like(trans)
+        _check(lib().dfold_rigid_apply_bwd(_ptr(quat), _ptr(trans), _ptr(pts), fs, _ptr(_f32c(dout)), _ptr(dpts), _ptr(dq), _ptr(dt),
+                                           F_, N_, m, int(ctx.inverse), _stream()), "dfold_rigid_apply_bwd")
+        if pts.shape[0] == 1 and F_ > 1:
+            dpts = dpts.sum(0, keepdim=True)
+        return dq, dt, dpts, None
+
+
+def rigid_apply(quat, trans, pts, inverse: bool = False):
+    """Apply frames (quaternion form) to points: ``R p + t`` or ``R^T (p - t)``.
+
+    quat [*,4], trans [*,3], pts [*, 3] broadcastable with one extra trailing point axis allowed
+    (the ``r[..., None].apply(pts)`` idiom)."""
+    _need_cuda(quat, trans, pts)
+    bshape = torch.broadcast_shapes(quat.shape[:-1], pts.shape[:-1])
+    if any(d == 0 for d in bshape):
+        return pts.new_zeros(bshape + (3,))
+    fdims = quat.dim() - 1
+    # frames = leading dims of quat that are not broadcast singleton; points = the rest
+    lead = bshape[:fdims]
+    # split lead into (frames with real quats) and trailing singleton dims of quat that the points fan out over
+    k = fdims
+    while k > 0 and quat.shape[k - 1] == 1 and bshape[k - 1] != 1:
+        k -= 1
+    fshape = tuple(bshape[:k])
+    mshape = tuple(bshape[k:])
+    nfr = 1
+    for d in fshape:
+        nfr *= d
+    m = 1
+    for d in mshape:
+        m *= d
+    q2 = _f32c(quat.expand(fshape + (1,) * (fdims - k) + (4,)).reshape(1, max(nfr, 1), 4))
+    t2 = _f32c(trans.expand(fshape + (1,) * (fdims - k) + (3,)).reshape(1, max(nfr, 1), 3))
+    p2 = _f32c(pts.expand(bshape + (3,)).reshape(1, max(nfr, 1), m, 3))
+    out = _RigidApplyFn.apply(q2, t2, p2, inverse)
+    return out.reshape(bshape + (3,))
+
+
+def ipa_points(raw, quat, trans, H: int):
+    """raw [Fs,N,3*H*P] (all x, then all y, then all z) -> global-frame points [F,N,H,P,3]."""
+    Fs, N_, W = raw.shape
+    hp = W // 3
+    pts = raw.reshape(Fs, N_, 3, hp).transpose(-1, -2).contiguous()          # [Fs,N,H*P,3]
+    out = _RigidApplyFn.apply(_f32c(quat), _f32c(trans), _f32c(pts), False)  # [F,N,H*P,3]
+    return out.reshape(out.shape[0], N_, H, hp // H, 3)
+
+
+class _ComposeFn(Function):
+    @staticmethod
+    def forward(ctx, quat, trans, upd, mask):
+        _need_cuda(quat, trans, upd, mask)
+        qc, tc, uc = _f32c(quat), _f32c(trans), _f32c(upd)
+        mc = _f32c(mask.expand(quat.shape[:-1] + (1,))) if mask is not None else None
+        n = qc.numel() // 4
+        qo, to = torch.empty_like(qc), torch.empty_like(tc)
+        _check(lib().dfold_compose_q_update_fwd(_ptr(qc), _ptr(tc), _ptr(uc), _ptr(mc), _ptr(qo), _ptr(to), n, _stream()),
+               "dfold_compose_q_update_fwd")
+        ctx.save_for_backward(qc, uc, mc)
+        return qo, to
+
+    @staticmethod
+    def backward(ctx, dqo, dto):
+        qc, uc, mc = ctx.saved_tensors
+        n = qc.numel() // 4
+        dq, dt, du = torch.empty_like(qc), torch.empty(qc.shape[:-1] + (3,), dtype=torch.float32, device=qc.device), torch.empty_like(uc)
+        _check(lib().dfold_compose_q_update_bwd(_ptr(qc), _ptr(uc), _ptr(mc), _ptr(_f32c(dqo)), _ptr(_f32c(dto)), _ptr(dq), _ptr(dt),
+                                                _ptr(du), n, _stream()), "dfold_compose_q_update_bwd")
+        return dq, dt, du, None
+
+
+def compose_q_update(quat, trans, upd6, mask=None):
+    """Backbone update: q' = normalise(q + m q*(0,u)), t' = t + m R(q) v with upd6 = (u, v); mask [...,1] or None."""
+    return _ComposeFn.apply(quat, trans, upd6, mask)
+
+
+def keep_last_frame(x):
+    """x with every leading-axis slice but the last replaced by zeros (reference ``rigid_update[:-1] *= 0``)."""
+    return torch.cat([torch.zeros_like(x[:-1]), x[-1:]], dim=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# invariant point attention
+# --------------------------------------------------------------------------------------------------
+class _QKLogitsFn(Function):
+    """logit0[f,h,i,j] = alpha * q[f,i,h,:] . k[f,j,h,:] + beta * b[f,h,i,j]   (k = first C of each kv head)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, b_hm, alpha, beta):
+        _need_cuda(q, kv, b_hm)
+        Fs, N_, H_, C_ = q.shape
+        Fz = b_hm.shape[0]
+        Fl = max(Fs, Fz)
+        q, kv = _f32c(q), _f32c(kv)
+        out = torch.empty((Fl, H_, N_, N_), dtype=torch.float32, device=q.device)
+        sb = b_hm.stride()
+        for f in range(Fl):
+            fq, fz = (f if Fs > 1 else 0), (f if Fz > 1 else 0)
+            _sgemm(q, fq * N_ * H_ * C_, H_ * C_, 1, C_, 0, kv, fq * N_ * H_ * 2 * C_, H_ * 2 * C_, 1, 2 * C_, 0,
+                   out, f * H_ * N_ * N_, N_, 1, N_ * N_, 0, N_, N_, C_,
+                   R=b_hm, r_off=fz * sb[0], r_rs=sb[2], r_cs=sb[3], r_bs=sb[1],
+                   batch=H_, alpha=alpha, beta=beta)
+        ctx.save_for_backward(q, kv)
+        ctx.meta = (alpha, beta, Fz, tuple(b_hm.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dl):
+        q, kv = ctx.saved_tensors
+        alpha, beta, Fz, bshape = ctx.meta
+        Fs, N_, H_, C_ = q.shape
+        dl = _f32c(dl)
+        Fl = dl.shape[0]
+        dq = torch.zeros_like(q)
+        dkv = torch.zeros_like(kv)
+        if Fs == 1 and Fl > 1:
+            dls = dl.sum(0, keepdim=True)
+        else:
+            dls = dl
+        for f in range(Fs):
+            # dq[n,h,c] = alpha sum_j dl[h,n,j] k[j,h,c]
+            _sgemm(dls, f * H_ * N_ * N_, N_, 1, N_ * N_, 0, kv, f * N_ * H_ * 2 * C_, 1, H_ * 2 * C_, 2 * C_, 0,
+                   dq, f * N_ * H_ * C_, H_ * C_, 1, C_, 0, N_, C_, N_, batch=H_, alpha=alpha)
+            # dk[j,h,c] = alpha sum_n dl[h,n,j] q[n,h,c]
+            _sgemm(dls, f * H_ * N_ * N_, 1, N_, N_ * N_, 0, q, f * N_ * H_ * C_, 1, H_ * C_, C_, 0,
+                   dkv, f * N_ * H_ * 2 * C_, H_ * 2 * C_, 1, 2 * C_, 0, N_, C_, N_, batch=H_, alpha=alpha)
+        db = beta * (dl if Fz > 1 or Fl == 1 else dl.sum(0, keepdim=True))
+        return dq, dkv, db.reshape(bshape) if db.shape != bshape else db, None, None
+
+
+def qk_logits(q, kv, b_hm, alpha: float, beta: float):
+    """Scalar part of the IPA logits, head-major [F,H,N,N].  q [Fs,N,H,C]; kv [Fs,N,H,2C]; b_hm [Fz,H,N,N] (any strides)."""
+    return _QKLogitsFn.apply(q, kv, b_hm, alpha, beta)
+
+
+class _IpaAttnFn(Function):
+    @staticmethod
+    def forward(ctx, logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps):
+        _need_cuda(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma)
+        logit0, kv, q_pts, kv_pts, pair = _f32c(logit0), _f32c(kv), _f32c(q_pts), _f32c(kv_pts), _f32c(pair)
+        quat, trans, mask, gamma = _f32c(quat), _f32c(trans), _f32c(mask), _f32c(gamma)
+        F_, N_, H_ = q_pts.shape[0], q_pts.shape[1], q_pts.shape[2]
+        C_ = kv.shape[-1] // 2
+        Cp = pair.shape[-1]
+        D = H_ * (C_ + (8 if dfold else 4) * Pv + Cp)
+        cat = torch.empty((F_, N_, D), dtype=torch.float32, device=q_pts.device)
+        lse = torch.empty((F_, H_, N_), dtype=torch.float32, device=q_pts.device)
+        args = _IpaAttnFn._args(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
+        _check(lib().dfold_ipa_attn_fwd(*args, _ptr(cat), _ptr(lse), _stream()), "dfold_ipa_attn_fwd")
+        ctx.save_for_backward(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, cat, lse)
+        ctx.meta = (Pq, Pv, dfold, inf, eps)
+        return cat
+
+    @staticmethod
+    def _args(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps):
+        l_fs = 0 if logit0.shape[0] == 1 else H_ * N_ * N_
+        kv_fs = 0 if kv.shape[0] == 1 else N_ * H_ * 2 * C_
+        p_fs = 0 if pair.shape[0] == 1 else N_ * N_ * Cp
+        return (_ptr(logit0), l_fs, _ptr(kv), kv_fs, _ptr(q_pts), _ptr(kv_pts), _ptr(pair), p_fs, _ptr(quat), _ptr(trans),
+                _ptr(mask), _ptr(gamma), F_, N_, H_, C_, Pq, Pv, Cp, int(dfold), inf, eps)
+
+    @staticmethod
+    def backward(ctx, dcat):
+        logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, cat, lse = ctx.saved_tensors
+        Pq, Pv, dfold, inf, eps = ctx.meta
+        F_, N_, H_ = q_pts.shape[0], q_pts.shape[1], q_pts.shape[2]
+        C_ = kv.shape[-1] // 2
+        Cp = pair.shape[-1]
+        PQ3, PV3 = 3 * Pq, 3 * Pv
+        D = cat.shape[-1]
+        dev = cat.device
+        dcat = _f32c(dcat)
+        new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        d_og, delta = new(F_, N_, H_, Pv, 3), new(F_, H_, N_)
+        Pm, dS = new(H_, F_, N_, N_), new(H_, F_, N_, N_)
+        dq_pts, dkv_pts = new(*q_pts.shape), new(*kv_pts.shape)
+        dquat, dtrans = new(*quat.shape), new(*trans.shape)
+        dgamma = torch.zeros(H_, dtype=torch.float32, device=dev)
+        args = _IpaAttnFn._args(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
+        _check(lib().dfold_ipa_attn_bwd(*args, _ptr(cat), _ptr(lse), _ptr(dcat), _ptr(d_og), _ptr(delta), _ptr(Pm), _ptr(dS),
+                                        _ptr(dq_pts), _ptr(dkv_pts), _ptr(dquat), _ptr(dtrans), _ptr(dgamma), _stream()),
+               "dfold_ipa_attn_bwd")
+        NN = N_ * N_
+        # ---- value gradient  dv[j,h,c] = sum_{f,i} P[h,f,i,j] dO[f,i,h,c] ----
+        Fs = kv.shape[0]
+        dkv = torch.zeros_like(kv)
+        if Fs == 1:
+            _sgemm(Pm, 0, 1, N_, F_ * NN, 0, dcat, 0, 1, D, C_, 0, dkv, C_, H_ * 2 * C_, 1, 2 * C_, 0,
+                   N_, C_, F_ * N_, batch=H_)
+        else:
+            _sgemm(Pm, 0, 1, N_, F_ * NN, NN, dcat, 0, 1, D, C_, N_ * D, dkv, C_, H_ * 2 * C_, 1, 2 * C_, N_ * H_ * 2 * C_,
+                   N_, C_, N_, batch=H_, batch2=F_)
+        # ---- value-point gradient  dvp[f,j,h,e] = sum_i P[h,f,i,j] d_og[f,i,h,e] ----
+        W = PQ3 + PV3
+        _sgemm(Pm, 0, 1, N_, F_ * NN, NN, d_og, 0, 1, H_ * PV3, PV3, N_ * H_ * PV3, dkv_pts, PQ3, H_ * W, 1, W, N_ * H_ * W,
+               N_, PV3, N_, batch=H_, batch2=F_)
+        # ---- pair gradient  dz[i,j,c] = sum_{h,f} P[h,f,i,j] dOpair[f,i,h,c] ----
+        offPair = H_ * C_ + 4 * H_ * Pv
+        dop = dcat[..., offPair:offPair + H_ * Cp].reshape(F_, N_, H_, Cp)
+        Fz = pair.shape[0]
+        dpair = torch.empty_like(pair)
+        if Fz == 1:
+            dop_hf = dop.permute(2, 0, 1, 3).contiguous()                     # [H,F,N,Cp]
+            _sgemm(Pm, 0, 1, NN, N_, 0, dop_hf, 0, 1, N_ * Cp, Cp, 0, dpair, 0, Cp, 1, N_ * Cp, 0, N_, Cp, H_ * F_, batch=N_)
+        else:
+            dop_fh = dop.permute(0, 2, 1, 3).contiguous()                     # [F,H,N,Cp]
+            _sgemm(Pm, 0, 1, F_ * NN, NN, N_, dop_fh, 0, 1, N_ * Cp, H_ * N_ * Cp, Cp, dpair, 0, Cp, 1, NN * Cp, N_ * Cp,
+                   N_, Cp, H_, batch=F_, batch2=N_)
+        # ---- logits ----
+        if logit0.shape[0] == 1:
+            dlogit0 = dS.sum(1).unsqueeze(0)
+        else:
+            dlogit0 = dS.permute(1, 0, 2, 3).contiguous()
+        return dlogit0, dkv, dq_pts, dkv_pts, dpair, dquat, dtrans, None, dgamma, None, None, None, None, None
+
+
+def ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, *, Pq, Pv, dfold, inf, eps):
+    """Fused IPA core -> concat buffer [F,N,D] in the reference's feature order (see csrc/ipa_attn.cu)."""
+    return _IpaAttnFn.apply(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps)

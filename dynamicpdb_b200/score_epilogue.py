@@ -1,0 +1,76 @@
+"""Closed-form score epilogue of the network as a diffuser-shaped object.
+
+``FullScoreNetwork(model_conf, diffuser)`` only needs two methods of the diffuser it is handed:
+``calc_rot_score(rots_t, rots_0, t)`` and ``calc_trans_score(trans_t, trans_0, t, use_torch=True, scale=True)``
+(reference src/data/se3_diffuser.py:115-125).  ``SE3ScoreDiffuser`` provides exactly those, with the same numerics
+as the reference path  se3_diffuser.calc_rot_score -> utils.quat_to_rotvec (src/data/utils.py:589-606) ->
+so3_diffuser.torch_score (:274-305, use_cached_score=False) -> igso3_expansion (:9-49) / score (:71-117), and
+r3_diffuser.score (:169-177) — but the sigma(t) lookup stays on the device (the reference does
+``du.move_to_np(t)``, a host synchronisation inside the model forward).  The reference's own ``SE3Diffuser`` can be
+passed instead; this class exists so bench / tests run where /root/reference is absent.
+"""
+import numpy as np
+import torch
+
+from . import rigid_utils as ru
+
+
+class SE3ScoreDiffuser:
+    def __init__(self, se3_conf):
+        so3, r3 = se3_conf.so3, se3_conf.r3
+        self.min_sigma, self.max_sigma, self.num_sigma = so3.min_sigma, so3.max_sigma, so3.num_sigma
+        self.min_b, self.max_b, self.coordinate_scaling = r3.min_b, r3.max_b, r3.coordinate_scaling
+        self.L = 1000
+        self._grid_np = self._sigma_np(np.linspace(0.0, 1.0, self.num_sigma))      # discrete_sigma, so3_diffuser.py:183
+        self._grid = {}
+
+    def _sigma_np(self, t):
+        return np.log(t * np.exp(self.max_sigma) + (1 - t) * np.exp(self.min_sigma))   # :192-199 (logarithmic)
+
+    def _sigma_of(self, t: torch.Tensor) -> torch.Tensor:
+        """sigma(t) snapped to the reference's 1000-point grid: discrete_sigma[digitize(sigma(t)) - 1]."""
+        dev = t.device
+        if dev not in self._grid:
+            self._grid[dev] = torch.from_numpy(self._grid_np).to(dev)
+        grid = self._grid[dev]
+        t64 = t.to(torch.float64)
+        s = torch.log(t64 * float(np.exp(self.max_sigma)) + (1 - t64) * float(np.exp(self.min_sigma)))
+        idx = torch.bucketize(s, grid, right=True) - 1
+        return grid[idx.clamp(0, grid.numel() - 1)]
+
+    # ---- se3_diffuser.py:119-125 ----
+    def calc_rot_score(self, rots_t, rots_0, t, eps: float = 1e-6):
+        quats_0_inv = rots_0.invert().get_quats()
+        quats_0t = ru.quat_multiply(quats_0_inv, rots_t.get_quats())
+        vec = _quat_to_rotvec(quats_0t)
+        omega = torch.linalg.norm(vec, dim=-1) + eps                      # fp32
+        sigma = self._sigma_of(t)[:, None, None]                          # fp64 [1,1,1]
+        ls = torch.arange(self.L, device=vec.device)[None, None]          # int64
+        om = omega[..., None]
+        half = ls + 1 / 2                                                 # fp32, as in the reference
+        decay = (2 * ls + 1) * torch.exp(-ls * (ls + 1) * sigma ** 2 / 2) # fp64
+        hi, lo = torch.sin(om * half), torch.sin(om / 2)
+        series = (decay * hi / lo).sum(dim=-1)
+        dhi, dlo = half * torch.cos(om * half), 0.5 * torch.cos(om / 2)
+        dseries = (decay * (lo * dhi - hi * dlo) / lo ** 2).sum(dim=-1)
+        norm = dseries / (series + 1e-4)
+        return norm[..., None] * vec / (omega[..., None] + eps)
+
+    # ---- se3_diffuser.py:115-117 -> r3_diffuser.py:169-177 ----
+    def calc_trans_score(self, trans_t, trans_0, t, use_torch=False, scale=True):
+        if scale:
+            trans_t = trans_t * self.coordinate_scaling
+            trans_0 = trans_0 * self.coordinate_scaling
+        beta = t * self.min_b + (1 / 2) * (t ** 2) * (self.max_b - self.min_b)
+        exp = torch.exp if use_torch else np.exp
+        return -(trans_t - exp(-1 / 2 * beta) * trans_0) / (1 - exp(-beta))
+
+
+def _quat_to_rotvec(quat, eps=1e-6):
+    quat = torch.where(quat[..., :1] < 0, -quat, quat)
+    angle = 2 * torch.atan2(torch.linalg.norm(quat[..., 1:], dim=-1), quat[..., 0])
+    a2 = angle * angle
+    small = 2 + a2 / 12 + 7 * a2 * a2 / 2880
+    large = angle / torch.sin(angle / 2 + eps)
+    is_small = (angle <= 1e-3).float()
+    return (small * is_small + (1 - is_small) * large)[..., None] * quat[..., 1:]

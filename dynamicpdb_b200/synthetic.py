@@ -1,0 +1,106 @@
+"""Seeded synthetic inputs and configs for the DFOLDv2 score network.
+
+Used by bench.py, __graft_entry__.smoke() and the tests; no dynamicPDB data exists in the container.
+Shapes follow the batch dict that reaches ``FullScoreNetwork.forward`` after the trainer's
+``[B,F,...] -> [B*F,...]`` flatten with B=1 (train_DFOLD_dynamics.py:680-684).
+"""
+import math
+from types import SimpleNamespace
+from typing import Dict
+
+import torch
+
+
+def model_conf(nf: int, *, c_s=256, c_z=128, c_hidden=256, no_heads=8, no_qk_points=8, no_v_points=12,
+               num_blocks=4, coordinate_scaling=1.0) -> SimpleNamespace:
+    """Attribute-style config with the fields the model reads (config/train_DFOLDv2.yaml:65-104)."""
+    ipa = SimpleNamespace(c_s=c_s, c_z=c_z, c_hidden=c_hidden, no_heads=no_heads, no_qk_points=no_qk_points,
+                          no_v_points=no_v_points, num_blocks=num_blocks, coordinate_scaling=coordinate_scaling)
+    embed = SimpleNamespace(DFOLDv2_embedder=True, index_embed_size=32)
+    return SimpleNamespace(node_embed_size=c_s, edge_embed_size=c_z, frame_time=nf, embed=embed, ipa=ipa)
+
+
+PRESET_A = dict(c_s=256, c_z=128, c_hidden=256, no_heads=8, no_qk_points=8, no_v_points=12)   # train_DFOLDv2.yaml
+PRESET_B = dict(c_s=256, c_z=128, c_hidden=16, no_heads=12, no_qk_points=4, no_v_points=8)    # train_DFOLDv2_new.yaml
+PRESET_TINY = dict(c_s=32, c_z=16, c_hidden=8, no_heads=2, no_qk_points=2, no_v_points=3)     # fast CPU tests
+
+
+def diffuser_conf(coordinate_scaling: float = 1.0) -> SimpleNamespace:
+    """config/train_DFOLDv2.yaml:43-63 (run_train.sh:24 overrides coordinate_scaling to 1.0)."""
+    so3 = SimpleNamespace(num_omega=1000, num_sigma=1000, min_sigma=0.1, max_sigma=1.5,
+                          schedule="logarithmic", cache_dir="/tmp/dfold_igso3_cache", use_cached_score=False)
+    r3 = SimpleNamespace(min_b=0.1, max_b=20.0, coordinate_scaling=coordinate_scaling)
+    return SimpleNamespace(diffuse_trans=True, diffuse_rot=True, r3=r3, so3=so3)
+
+
+def _unit(x):
+    return x / torch.linalg.norm(x, dim=-1, keepdim=True)
+
+
+def _quat_mul(a, b):
+    aw, ax, ay, az = a.unbind(-1)
+    bw, bx, by, bz = b.unbind(-1)
+    return torch.stack([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                        aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw], dim=-1)
+
+
+def make_feats(nf: int, n_res: int, *, seed: int = 0, node_dim: int = 256, edge_dim: int = 128, t: float = 0.5,
+               coordinate_scaling: float = 1.0, device="cpu", loader_dtypes: bool = False) -> Dict[str, torch.Tensor]:
+    """One protein window of ``nf`` consecutive trajectory frames.
+
+    Frame 0: random unit quaternions on a 3.8 A C-alpha random walk (centred); frame f = frame f-1 composed with a
+    small rigid motion (rotvec sigma 0.02 rad, translation sigma 0.1 A), i.e. ~1 ps MD spacing.
+    ``loader_dtypes=True`` reproduces the float64 fields the reference's loader emits (Appendix B).
+    """
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    q = _unit(rn(n_res, 4))
+    steps = _unit(rn(n_res, 3)) * 3.8
+    ca = torch.cumsum(steps, dim=0)
+    ca = ca - ca.mean(0, keepdim=True)
+    rig = [torch.cat([q, ca], dim=-1)]
+    for _ in range(1, nf):
+        rv = rn(n_res, 3) * 0.02
+        ang = torch.linalg.norm(rv, dim=-1, keepdim=True)
+        dq = torch.cat([torch.cos(ang / 2), rv / ang * torch.sin(ang / 2)], dim=-1)
+        q = _unit(_quat_mul(q, dq))
+        ca = ca + rn(n_res, 3) * 0.1
+        rig.append(torch.cat([q, ca], dim=-1))
+    rigids_0 = torch.stack(rig, dim=0)
+    rigids_t = torch.cat([_unit(rn(nf, n_res, 4)), rn(nf, n_res, 3) / coordinate_scaling], dim=-1)
+    ang = rn(nf, n_res, 7) * math.pi
+    f64 = torch.float64 if loader_dtypes else torch.float32
+    feats = {
+        "res_mask": torch.ones(nf, n_res),
+        "fixed_mask": torch.zeros(nf, n_res),
+        "seq_idx": torch.arange(1, n_res + 1).unsqueeze(0).repeat(nf, 1),
+        "t": torch.tensor([t], dtype=f64),
+        "rigids_0": rigids_0,
+        "rigids_t": rigids_t,
+        "force": rn(nf, n_res, 3).to(f64),
+        "vel": rn(nf, n_res, 3).to(f64),
+        "node_repr": rn(n_res, node_dim),
+        "edge_repr": rn(n_res, n_res, edge_dim),
+        "torsion_angles_sin_cos": torch.stack([torch.sin(ang), torch.cos(ang)], dim=-1).to(f64),
+        "torsion_angles_mask": torch.ones(nf, n_res, 7, dtype=f64),
+        "aatype": torch.randint(0, 20, (nf, n_res), generator=g),
+        "sc_ca_t": torch.zeros(nf, n_res, 3),
+    }
+    return {k: v.to(device) for k, v in feats.items()}
+
+
+def dezero_(state: Dict[str, torch.Tensor], seed: int = 1, std: float = 0.02) -> None:
+    """Redraw every all-zero *weight* (the reference's 'final' init: IPA linear_out, bb_update, AngleResnet
+    linear_2) from N(0, std^2) so parity is not vacuous."""
+    g = torch.Generator().manual_seed(seed)
+    for k in sorted(state):
+        v = state[k]
+        if k.endswith("weight") and v.dtype.is_floating_point and v.numel() > 0 and not bool(v.any()):
+            v.copy_(torch.randn(v.shape, generator=g) * std)
+
+
+def surrogate_loss(out: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Mean squares of the trained-on outputs; the reference's loss_fn needs the trainer."""
+    return ((out["rigids"] ** 2).mean() + (out["angles"] * out["unorm_angles"]).mean()
+            + (out["unorm_angles"] ** 2).mean()
+            + (out["rot_score"].float() ** 2).mean() + (out["trans_score"].float() ** 2).mean())

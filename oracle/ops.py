@@ -1,0 +1,99 @@
+"""Plain-torch (CPU-capable) statements of each operator in dynamicpdb_b200/kernels.py, with the same signatures.
+
+TEST INFRASTRUCTURE: tests monkey-patch ``dynamicpdb_b200.kernels.<op>`` with these to exercise the product's
+host-side module logic without a GPU, and the ``-m gpu`` tests compare each CUDA op against them.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import dfold_oracle as O
+
+
+def linear(x, weight, bias=None, act=None, residual=None, pre_relu=False):
+    if pre_relu:
+        x = F.relu(x)
+    y = F.linear(x.to(weight.dtype), weight, bias)
+    if act == "relu":
+        y = F.relu(y)
+    elif act == "silu":
+        y = F.silu(y)
+    return y if residual is None else y + residual
+
+
+def conv5x5(x, weight, bias=None, relu=True, residual=None):
+    y = F.conv2d(x.permute(2, 0, 1).unsqueeze(0), weight, bias, padding=(weight.shape[2] // 2, weight.shape[3] // 2))
+    y = y.squeeze(0).permute(1, 2, 0)
+    if relu:
+        y = F.relu(y)
+    return y if residual is None else y + residual
+
+
+def global_layernorm(x, eps=1e-4, silu=False):
+    y = O.my_layernorm(x, eps)
+    return F.silu(y) if silu else y
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    return F.layer_norm(x, x.shape[-1:], weight, bias, eps)
+
+
+def quat_to_rot(q):
+    return O.quat_to_rot(q)
+
+
+def rigid_apply(quat, trans, pts, inverse=False):
+    rig = torch.cat([quat, trans], dim=-1)
+    return O.rigid_invert_apply(rig, pts) if inverse else O.rigid_apply(rig, pts)
+
+
+def ipa_points(raw, quat, trans, H):
+    Fs, N, W = raw.shape
+    hp = W // 3
+    pts = raw.reshape(Fs, N, 3, hp).transpose(-1, -2)
+    out = rigid_apply(quat[:, :, None, :], trans[:, :, None, :], pts)
+    return out.reshape(out.shape[0], N, H, hp // H, 3)
+
+
+def compose_q_update(quat, trans, upd6, mask=None):
+    r = O.compose_q_update_vec(torch.cat([quat, trans], dim=-1), upd6, mask)
+    return r[..., :4], r[..., 4:]
+
+
+def keep_last_frame(x):
+    return torch.cat([torch.zeros_like(x[:-1]), x[-1:]], dim=0)
+
+
+def qk_logits(q, kv, b_hm, alpha, beta):
+    C = q.shape[-1]
+    k = kv[..., :C]
+    return alpha * torch.einsum("fihc,fjhc->fhij", q, k) + beta * b_hm
+
+
+def ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, *, Pq, Pv, dfold, inf, eps):
+    Fn, N, H = q_pts.shape[:3]
+    C = kv.shape[-1] // 2
+    v = kv[..., C:]
+    k_pts, v_pts = kv_pts[..., :Pq, :], kv_pts[..., Pq:, :]
+    d = q_pts[:, :, None] - k_pts[:, None, :]                       # [F,i,j,H,Pq,3]
+    pt = ((d * d).sum(-1) * gamma[:, None]).sum(-1) * (-0.5)          # [F,i,j,H]
+    a = logit0 + pt.permute(0, 3, 1, 2) + (inf * (mask[:, :, None] * mask[:, None, :] - 1))[:, None]
+    a = torch.softmax(a, dim=-1)
+    o = torch.einsum("fhij,fjhc->fihc", a, v.expand(Fn, -1, -1, -1)).reshape(Fn, N, H * C)
+    og = torch.einsum("fhij,fjhpx->fihpx", a, v_pts)
+    rig = torch.cat([quat, trans], dim=-1)
+    ol = O.rigid_invert_apply(rig[:, :, None, None, :], og)
+    nl = torch.sqrt((ol ** 2).sum(-1) + eps).reshape(Fn, N, H * Pv)
+    ng = torch.sqrt((og ** 2).sum(-1) + eps).reshape(Fn, N, H * Pv)
+    ol, og = ol.reshape(Fn, N, H * Pv, 3), og.reshape(Fn, N, H * Pv, 3)
+    pz = pair.expand(Fn, -1, -1, -1)
+    o_pair = torch.einsum("fhij,fijc->fihc", a, pz).reshape(Fn, N, -1)
+    feats = [o, ol[..., 0], ol[..., 1], ol[..., 2], nl, o_pair]
+    if dfold:
+        feats += [og[..., 0], og[..., 1], og[..., 2], ng]
+    return torch.cat(feats, dim=-1)
+
+
+ALL = ["linear", "conv5x5", "global_layernorm", "layer_norm", "quat_to_rot", "rigid_apply", "ipa_points",
+       "compose_q_update", "keep_last_frame", "qk_logits", "ipa_attention"]
