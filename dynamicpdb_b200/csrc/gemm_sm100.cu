@@ -13,7 +13,11 @@
 //               out-of-bounds zero fill, so the convolution needs no im2col and no padding buffer.
 //   warp 1      tcgen05.mma issuer (one elected lane): 3 products x 4 K-steps of UMMA 128xBNx16 per stage,
 //               accumulator in TMEM; tcgen05.commit releases the smem stage / signals the epilogue.
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns, bias / activation / residual, fp32 stores.
+//   warps 2..9  accumulate + epilogue.  The tensor core's fp32 accumulator TRUNCATES on every MMA (measured on
+//               B200: relative bias -1e-4 at K = 32000, growing linearly with the number of MMAs), so a TMEM
+//               accumulator only ever holds kChunk = 4 k-blocks (48 MMAs).  Two TMEM accumulators ping-pong: while
+//               the MMA warp fills one, these warps tcgen05.ld the other and add it into fp32 registers with
+//               round-to-nearest CUDA-core adds, then apply bias / activation / residual and store.
 //
 // Replaces (reference file:line): nn.Linear in src/model/ipa_pytorch_dynamic.py:284-305,757-796,590,
 // openfold/model/structure_module.py:102-110,58-59; nn.Conv2d stack src/model/ipa_pytorch_dynamic.py:664-706.
@@ -26,7 +30,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;     // 2 control warps + 8 accumulate/epilogue warps
+constexpr int kChunk = 4;         // k-blocks accumulated in TMEM before promotion to registers
 
 template <int BN> struct TileCfg {
     static constexpr int kStages = (BN >= 256) ? 2 : ((BN >= 128) ? 3 : 4);
@@ -34,7 +39,7 @@ template <int BN> struct TileCfg {
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr int kTmemCols = (BN <= 32) ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    static constexpr int kTmemCols = 2 * BN;                  // two ping-pong accumulators (power of two >= 32)
 };
 
 struct GemmParams {
@@ -60,6 +65,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -117,6 +125,19 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major, 128B-swizzled operand tile (weight-gradient mode): the tile is stored [k][mn] with 64 mn-elements
+// (128 B) contiguous per k row; 8 k-rows form a 1024 B swizzle atom (SBO), 64-wide mn atoms are 64 rows x 128 B
+// = 8192 B apart (LBO).
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(8192 >> 4) << 16;                  // leading byte offset: next 64-wide mn atom
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next group of 8 k rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -126,11 +147,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;   // 8-byte aligned
-    // barrier layout: full[kStages], empty[kStages], tmem_full, then the tmem pointer word
+    // barrier layout: full[kStages], empty[kStages], acc_full[2], acc_empty[2], then the tmem pointer word
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * Cfg::kStages);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 1);
+    auto acc_full_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + b); };
+    auto acc_empty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -150,7 +172,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -184,13 +206,22 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     tma_load_3d(sb_hi, &map_b_hi, full_bar(s), c * BK, col0, tap);
                     tma_load_3d(sb_lo, &map_b_lo, full_bar(s), c * BK, col0, tap);
                 } else {
+                    // K runs over pixels (f, 64-residue block j); operands are MN-major: boxes of
+                    // 64 channels x 64 residues, one per 64-wide channel atom.  The tap shift is on the
+                    // residue / frame coordinates (row dimensions), out-of-image rows are zero-filled.
                     const int f = kb / p.kc, j = kb % p.kc;
                     const int dn = tap_z % p.taps_n - p.taps_n / 2;
                     const int df = tap_z / p.taps_n - p.taps_f / 2;
-                    tma_load_3d(sa_hi, &map_a_hi, full_bar(s), j * BK, f, m0);
-                    tma_load_3d(sa_lo, &map_a_lo, full_bar(s), j * BK, f, m0);
-                    tma_load_3d(sb_hi, &map_b_hi, full_bar(s), j * BK + dn, f + df, col0);
-                    tma_load_3d(sb_lo, &map_b_lo, full_bar(s), j * BK + dn, f + df, col0);
+#pragma unroll
+                    for (int a = 0; a < BM / 64; ++a) {
+                        tma_load_3d(sa_hi + a * 8192, &map_a_hi, full_bar(s), m0 + a * 64, j * BK, f);
+                        tma_load_3d(sa_lo + a * 8192, &map_a_lo, full_bar(s), m0 + a * 64, j * BK, f);
+                    }
+#pragma unroll
+                    for (int b = 0; b < BN / 64; ++b) {
+                        tma_load_3d(sb_hi + b * 8192, &map_b_hi, full_bar(s), col0 + b * 64, j * BK + dn, f + df);
+                        tma_load_3d(sb_lo + b * 8192, &map_b_lo, full_bar(s), col0 + b * 64, j * BK + dn, f + df);
+                    }
                 }
             }
         }
@@ -198,34 +229,69 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const bool mn_major = (p.mode == 1);
+            if (mn_major) idesc |= (1u << 15) | (1u << 16);     // A and B are MN-major in weight-gradient mode
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 const int s = kb % Cfg::kStages;
                 const uint32_t ph = (kb / Cfg::kStages) & 1;
+                const int chunk = kb / kChunk;
+                const int buf = chunk & 1;
+                const bool chunk_start = (kb % kChunk) == 0;
+                if (chunk_start) {
+                    // the accumulate warps must have drained this TMEM buffer (two chunks ago)
+                    mbar_wait(acc_empty_bar(buf), ((chunk >> 1) & 1) ^ 1u);
+                    tcgen05_fence_after();
+                }
                 mbar_wait(full_bar(s), ph);
                 tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
                 const uint32_t sa_hi = smem_base + s * Cfg::kStageBytes;
                 const uint32_t sa_lo = sa_hi + Cfg::kABytes;
                 const uint32_t sb_hi = sa_lo + Cfg::kABytes;
                 const uint32_t sb_lo = sb_hi + Cfg::kBBytes;
-                const uint64_t da_hi = make_sw128_desc(sa_hi), da_lo = make_sw128_desc(sa_lo);
-                const uint64_t db_hi = make_sw128_desc(sb_hi), db_lo = make_sw128_desc(sb_lo);
+                const uint64_t da_hi = mn_major ? make_sw128_mn_desc(sa_hi) : make_sw128_desc(sa_hi);
+                const uint64_t da_lo = mn_major ? make_sw128_mn_desc(sa_lo) : make_sw128_desc(sa_lo);
+                const uint64_t db_hi = mn_major ? make_sw128_mn_desc(sb_hi) : make_sw128_desc(sb_hi);
+                const uint64_t db_lo = mn_major ? make_sw128_mn_desc(sb_lo) : make_sw128_desc(sb_lo);
+                // per K step (16 elements): K-major +32 B inside the swizzle row; MN-major +2 groups of 8 k rows
+                const uint64_t kstep = mn_major ? (uint64_t)((2 * 1024) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step, in 16 B units
-                    umma_bf16(tmem_base, da_lo + koff, db_hi + koff, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_bf16(tmem_base, da_hi + koff, db_lo + koff, idesc, 1u);
-                    umma_bf16(tmem_base, da_hi + koff, db_hi + koff, idesc, 1u);
+                    const uint64_t koff = kstep * k;
+                    umma_bf16(tmem_d, da_lo + koff, db_hi + koff, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                    umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, 1u);
                 }
                 umma_commit(empty_bar(s));      // smem stage reusable once these MMAs retire
+                if ((kb % kChunk) == kChunk - 1 || kb == p.num_kb - 1)
+                    umma_commit(acc_full_bar(buf));   // this chunk's partial sum is complete
             }
-            umma_commit(tmem_full_bar);         // accumulator complete
         }
     } else {
-        // =============================== epilogue (warps 2..5) ===============================
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
+        // =============================== accumulate + epilogue (warps 2..9) ===============================
+        constexpr int HALF = BN / 2;                    // columns owned by this warp
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;               // which half of the tile's columns
+        float acc[HALF];
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+        const int nchunks = (p.num_kb + kChunk - 1) / kChunk;
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(acc_full_bar(buf), (chunk >> 1) & 1);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF + c0), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[c0 + i] += __uint_as_float(v[i]);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty_bar(buf));
+        }
         const int r = q * 32 + lane;                    // row inside the tile
         long grow;                                      // global output row
         bool row_ok;
@@ -241,34 +307,31 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const float* rrow = p.res ? p.res + grow * p.ldr : nullptr;
         const bool vec_ok = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                             (p.out_tap_stride % 4 == 0);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (!row_ok) continue;
-            const int gc0 = col0 + c0;
-            if (gc0 >= p.n_out) continue;
-            float o[32];
+        if (row_ok) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(v[i]) * p.alpha;
-                const int gc = gc0 + i;
-                if (gc < p.n_out) {
-                    if (p.bias) x += __ldg(p.bias + gc);
-                    if (p.act == 1) x = fmaxf(x, 0.f);
-                    else if (p.act == 2) x = x / (1.f + __expf(-x));
-                    if (rrow) x += p.beta * __ldg(rrow + gc);
+            for (int c0 = 0; c0 < HALF; c0 += 4) {
+                const int gc0 = col0 + half * HALF + c0;
+                if (gc0 >= p.n_out) break;
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float x = acc[c0 + i] * p.alpha;
+                    const int gc = gc0 + i;
+                    if (gc < p.n_out) {
+                        if (p.bias) x += __ldg(p.bias + gc);
+                        if (p.act == 1) x = fmaxf(x, 0.f);
+                        else if (p.act == 2) x = x / (1.f + __expf(-x));
+                        if (rrow) x += p.beta * __ldg(rrow + gc);
+                    }
+                    o[i] = x;
                 }
-                o[i] = x;
-            }
-            if (vec_ok && gc0 + 32 <= p.n_out) {
+                if (vec_ok && gc0 + 4 <= p.n_out) {
+                    *reinterpret_cast<float4*>(orow + gc0) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(orow + gc0 + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (gc0 + i < p.n_out) orow[gc0 + i] = o[i];
+                    for (int i = 0; i < 4; ++i)
+                        if (gc0 + i < p.n_out) orow[gc0 + i] = o[i];
+                }
             }
         }
         tcgen05_fence_before();
@@ -378,21 +441,23 @@ extern "C" int dfold_gemm_bf16x3(
     return launch<64>(maps, p, grid, st);
 }
 
-// out[tap][m][n] = sum_{f, j} At[m][f][j] * Bt[n][f + df(tap)][j + dn(tap)]      (weight gradient; K = pixels)
+// out[tap][m][n] = alpha * sum_{f, j} A[f][j][m] * B[f + df(tap)][j + dn(tap)][n]      (weight gradient; K = pixels)
+// A planes [F][Nr][lda] (e.g. the gated output gradient, m = output channel), B planes [F][Nr][ldb] (the layer input,
+// n = input channel): the SAME pixel-major planes the forward / data-gradient GEMMs use, read MN-major.
 extern "C" int dfold_gemm_wgrad_bf16x3(
-    const uint16_t* at_hi, const uint16_t* at_lo, long M,
-    const uint16_t* bt_hi, const uint16_t* bt_lo, long Nn,
-    long F, long Nr, long ldp, int taps_f, int taps_n,
+    const uint16_t* a_hi, const uint16_t* a_lo, long M, long lda,
+    const uint16_t* b_hi, const uint16_t* b_lo, long Nn, long ldb,
+    long F, long Nr, int taps_f, int taps_n,
     float* out, long ldo, float alpha, void* stream) {
     DFOLD_REQUIRE(M > 0 && Nn > 0 && F > 0 && Nr > 0, "dfold_gemm_wgrad_bf16x3: empty problem");
-    DFOLD_REQUIRE(ldp % 8 == 0, "dfold_gemm_wgrad_bf16x3: ldp must be a multiple of 8 (got %ld)", ldp);
+    DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dfold_gemm_wgrad_bf16x3: lda/ldb must be multiples of 8 (got %ld, %ld)", lda, ldb);
     const int bn = pick_bn(Nn);
     CUtensorMap maps[4];
-    // planes are [rows][F][ldp]; dims (Nr, F, rows)
-    if (make_map(&maps[0], at_hi, Nr, F, M, ldp, F * ldp, BK, 1, BM)) return 1;
-    if (make_map(&maps[1], at_lo, Nr, F, M, ldp, F * ldp, BK, 1, BM)) return 1;
-    if (make_map(&maps[2], bt_hi, Nr, F, Nn, ldp, F * ldp, BK, 1, bn)) return 1;
-    if (make_map(&maps[3], bt_lo, Nr, F, Nn, ldp, F * ldp, BK, 1, bn)) return 1;
+    // dims (channel, residue, frame); boxes of 64 channels x 64 residues
+    if (make_map(&maps[0], a_hi, M, Nr, F, lda, Nr * lda, 64, BK, 1)) return 1;
+    if (make_map(&maps[1], a_lo, M, Nr, F, lda, Nr * lda, 64, BK, 1)) return 1;
+    if (make_map(&maps[2], b_hi, Nn, Nr, F, ldb, Nr * ldb, 64, BK, 1)) return 1;
+    if (make_map(&maps[3], b_lo, Nn, Nr, F, ldb, Nr * ldb, 64, BK, 1)) return 1;
     GemmParams p{};
     p.mode = 1;
     p.kc = (int)cdiv(Nr, BK);

@@ -38,7 +38,7 @@ _SIGS = {
     "dfold_compose_q_update_fwd": "pppppplp",
     "dfold_compose_q_update_bwd": "pppppppplp",
     "dfold_gemm_bf16x3": "ppllll" + "ppllii" + "pl" + "p" + "pl" + "ffi" + "p",
-    "dfold_gemm_wgrad_bf16x3": "ppl" + "ppl" + "lllii" + "plf" + "p",
+    "dfold_gemm_wgrad_bf16x3": "ppll" + "ppll" + "llii" + "plf" + "p",
     "dfold_ipa_attn_fwd": "plplppplpppp" + "iiiiiiii" + "ff" + "ppp",
     "dfold_ipa_attn_bwd": "plplppplpppp" + "iiiiiiii" + "ff" + "ppp" + "ppppppppp" + "p",
 }
@@ -171,7 +171,8 @@ def _conv_planes(w: torch.Tensor):
         i8, o8 = _pad8(I), _pad8(O)
         mk = lambda *s: torch.zeros(s, dtype=torch.int16, device=w.device)
         f_hi, f_lo, d_hi, d_lo = mk(T, O, i8), mk(T, O, i8), mk(T, I, o8), mk(T, I, o8)
-        _check(lib().dfold_conv_weight_prep(_ptr(_f32c(w.detach())), O, I, T, _ptr(f_hi), _ptr(f_lo), i8,
+        wc = _f32c(w.detach())     # keep the converted tensor alive until the launch is enqueued
+        _check(lib().dfold_conv_weight_prep(_ptr(wc), O, I, T, _ptr(f_hi), _ptr(f_lo), i8,
                                             _ptr(d_hi), _ptr(d_lo), o8, _stream()), "dfold_conv_weight_prep")
         return f_hi, f_lo, d_hi, d_lo
     return _cache_get("conv", w, build)
@@ -183,8 +184,8 @@ def _gemm(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out
            "dfold_gemm_bf16x3")
 
 
-def _gemm_wgrad(at, M, bt, Nn, F, Nr, ldp, taps_f, taps_n, out, ldo):
-    _check(lib().dfold_gemm_wgrad_bf16x3(_ptr(at[0]), _ptr(at[1]), M, _ptr(bt[0]), _ptr(bt[1]), Nn, F, Nr, ldp, taps_f, taps_n,
+def _gemm_wgrad(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo):
+    _check(lib().dfold_gemm_wgrad_bf16x3(_ptr(a[0]), _ptr(a[1]), M, lda, _ptr(b[0]), _ptr(b[1]), Nn, ldb, F, Nr, taps_f, taps_n,
                                          _ptr(out), ldo, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3")
 
 
@@ -238,16 +239,16 @@ class _LinearFn(Function):
         dx = dw = db = None
         if tc:
             db_buf = torch.zeros(N_, dtype=torch.float32, device=g.device) if need_b else None
-            (g_hi, g_lo), (gt_hi, gt_lo) = _split2d(g, gate=gate, want=need_x, want_t=need_w, colsum=db_buf)
+            (g_hi, g_lo), _ = _split2d(g, gate=gate, want=need_x or need_w, colsum=db_buf)
             db = db_buf
             if need_x:
                 _, _, wt_hi, wt_lo = _linear_planes(w)
                 dx = torch.empty((M_, K_), dtype=torch.float32, device=g.device)
                 _gemm(g_hi, g_lo, 1, M_, N_, g_hi.shape[1], wt_hi, wt_lo, K_, wt_hi.shape[1], 1, 1, dx, K_, None, None, 0, 1.0, 0.0, 0)
             if need_w:
-                _, (xt_hi, xt_lo) = _split2d(x2, pre_relu=pre_relu, want=False, want_t=True)
+                (x_hi, x_lo), _ = _split2d(x2, pre_relu=pre_relu)
                 dw = torch.empty((N_, K_), dtype=torch.float32, device=g.device)
-                _gemm_wgrad((gt_hi, gt_lo), N_, (xt_hi, xt_lo), K_, 1, M_, gt_hi.shape[1], 1, 1, dw, K_)
+                _gemm_wgrad((g_hi, g_lo), N_, g_hi.shape[1], (x_hi, x_lo), K_, x_hi.shape[1], 1, M_, 1, 1, dw, K_)
         else:
             if gate is not None:
                 g = g * (gate > 0)
@@ -279,21 +280,6 @@ def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, pre_r
 # --------------------------------------------------------------------------------------------------
 # 5x5 (frame x residue) convolution, channels-last, implicit GEMM
 # --------------------------------------------------------------------------------------------------
-def _frame_transposed_planes(x2: torch.Tensor, F: int, N: int, gate=None, colsum=None):
-    """x2 [F*N, C] -> bf16 planes laid out [C][F][N8] (N8 = N rounded to 8) for the weight-gradient GEMM."""
-    C = x2.shape[1]
-    n8 = _pad8(N)
-    if n8 == N:
-        _, (hit, lot) = _split2d(x2, gate=gate, want=False, want_t=True, colsum=colsum)
-        return hit, lot, n8
-    hit = torch.empty((C, F, n8), dtype=torch.int16, device=x2.device)
-    lot = torch.empty((C, F, n8), dtype=torch.int16, device=x2.device)
-    for f in range(F):
-        _split2d(x2[f * N:(f + 1) * N], gate=None if gate is None else gate[f * N:(f + 1) * N], want=False, want_t=True,
-                 colsum=colsum, t_out=(hit, lot), t_ld=F * n8, t_off=f * n8, rpad=n8)
-    return hit, lot, n8
-
-
 class _Conv5x5Fn(Function):
     @staticmethod
     def forward(ctx, x, w, b, relu, residual):
@@ -325,19 +311,17 @@ class _Conv5x5Fn(Function):
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], has_b and ctx.needs_input_grad[2]
         dx = dw = db = None
         db_buf = torch.zeros(Co, dtype=torch.float32, device=g.device) if need_b else None
-        if need_x or need_b:
-            (g_hi, g_lo), _ = _split2d(g, gate=gate, want=need_x, colsum=db_buf)
-            db = db_buf
+        (g_hi, g_lo), _ = _split2d(g, gate=gate, want=need_x or need_w, colsum=db_buf)
+        db = db_buf
         if need_x:
             _, _, d_hi, d_lo = _conv_planes(w)
             dx = torch.empty((F_ * N_, Ci), dtype=torch.float32, device=g.device)
             _gemm(g_hi, g_lo, F_, N_, Co, Co, d_hi, d_lo, Ci, d_hi.shape[2], kh, kw, dx, Ci, None, None, 0, 1.0, 0.0, 0)
             dx = dx.reshape(F_, N_, Ci)
         if need_w:
-            gt_hi, gt_lo, n8 = _frame_transposed_planes(g, F_, N_, gate=gate)
-            xt_hi, xt_lo, _ = _frame_transposed_planes(x2, F_, N_)
+            (x_hi, x_lo), _ = _split2d(x2)
             taps = torch.empty((kh * kw, Co, Ci), dtype=torch.float32, device=g.device)
-            _gemm_wgrad((gt_hi, gt_lo), Co, (xt_hi, xt_lo), Ci, F_, N_, n8, kh, kw, taps, Ci)
+            _gemm_wgrad((g_hi, g_lo), Co, Co, (x_hi, x_lo), Ci, Ci, F_, N_, kh, kw, taps, Ci)
             dw = torch.empty((Co, Ci, kh, kw), dtype=torch.float32, device=g.device)
             _check(lib().dfold_taps_to_param(_ptr(taps), Co, Ci, kh * kw, _ptr(dw), _stream()), "dfold_taps_to_param")
         return dx, dw, db, None, (dy if has_r else None)
@@ -390,7 +374,8 @@ class _RowLNFn(Function):
         x2 = _f32c(x.reshape(-1, C))
         y = torch.empty_like(x2)
         stats = torch.empty((x2.shape[0], 2), dtype=torch.float32, device=x.device)
-        _check(lib().dfold_row_layernorm_fwd(_ptr(x2), _ptr(_f32c(w)), _ptr(_f32c(b)), _ptr(y), _ptr(stats), x2.shape[0], C, eps, _stream()),
+        wc, bc = _f32c(w), _f32c(b)
+        _check(lib().dfold_row_layernorm_fwd(_ptr(x2), _ptr(wc), _ptr(bc), _ptr(y), _ptr(stats), x2.shape[0], C, eps, _stream()),
                "dfold_row_layernorm_fwd")
         ctx.save_for_backward(x2, w, stats)
         ctx.shape = x.shape
@@ -404,7 +389,8 @@ class _RowLNFn(Function):
         dx = torch.empty_like(x2)
         dw = torch.zeros(C, dtype=torch.float32, device=x2.device)
         db = torch.zeros(C, dtype=torch.float32, device=x2.device)
-        _check(lib().dfold_row_layernorm_bwd(_ptr(x2), _ptr(_f32c(w)), _ptr(g), _ptr(stats), _ptr(dx), _ptr(dw), _ptr(db), x2.shape[0], C, _stream()),
+        wc = _f32c(w)
+        _check(lib().dfold_row_layernorm_bwd(_ptr(x2), _ptr(wc), _ptr(g), _ptr(stats), _ptr(dx), _ptr(dw), _ptr(db), x2.shape[0], C, _stream()),
                "dfold_row_layernorm_bwd")
         return dx.reshape(ctx.shape), dw, db, None
 
@@ -431,7 +417,8 @@ class _QuatToRotFn(Function):
     def backward(ctx, dR):
         (qc,) = ctx.saved_tensors
         dq = torch.empty_like(qc)
-        _check(lib().dfold_quat_to_rot_bwd(_ptr(qc), _ptr(_f32c(dR)), _ptr(dq), qc.numel() // 4, _stream()), "dfold_quat_to_rot_bwd")
+        gR = _f32c(dR)
+        _check(lib().dfold_quat_to_rot_bwd(_ptr(qc), _ptr(gR), _ptr(dq), qc.numel() // 4, _stream()), "dfold_quat_to_rot_bwd")
         return dq
 
 
@@ -465,7 +452,8 @@ class _RigidApplyFn(Function):
         dpts = torch.empty((F_, N_, m, 3), dtype=torch.float32, device=quat.device)
         dq = torch.empty_like(quat)
         dt = torch.empty_like(trans)
-        _check(lib().dfold_rigid_apply_bwd(_ptr(quat), _ptr(trans), _ptr(pts), fs, _ptr(_f32c(dout)), _ptr(dpts), _ptr(dq), _ptr(dt),
+        gout = _f32c(dout)
+        _check(lib().dfold_rigid_apply_bwd(_ptr(quat), _ptr(trans), _ptr(pts), fs, _ptr(gout), _ptr(dpts), _ptr(dq), _ptr(dt),
                                            F_, N_, m, int(ctx.inverse), _stream()), "dfold_rigid_apply_bwd")
         if pts.shape[0] == 1 and F_ > 1:
             dpts = dpts.sum(0, keepdim=True)
@@ -530,7 +518,8 @@ class _ComposeFn(Function):
         qc, uc, mc = ctx.saved_tensors
         n = qc.numel() // 4
         dq, dt, du = torch.empty_like(qc), torch.empty(qc.shape[:-1] + (3,), dtype=torch.float32, device=qc.device), torch.empty_like(uc)
-        _check(lib().dfold_compose_q_update_bwd(_ptr(qc), _ptr(uc), _ptr(mc), _ptr(_f32c(dqo)), _ptr(_f32c(dto)), _ptr(dq), _ptr(dt),
+        gq, gt = _f32c(dqo), _f32c(dto)    # both must stay alive: two temporaries may otherwise share one block
+        _check(lib().dfold_compose_q_update_bwd(_ptr(qc), _ptr(uc), _ptr(mc), _ptr(gq), _ptr(gt), _ptr(dq), _ptr(dt),
                                                 _ptr(du), n, _stream()), "dfold_compose_q_update_bwd")
         return dq, dt, du, None
 

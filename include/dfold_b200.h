@@ -1,0 +1,143 @@
+/* dfold_b200 — C ABI of the B200-native (sm_100a) DFOLDv2 score-network hot path.
+ *
+ * The reference (fudan-generative-vision/dynamicPDB) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary a maintainer binds is this shared library (libdfold_b200.so), loaded with ctypes by
+ * dynamicpdb_b200/kernels.py.  Every entry point cites the reference code it replaces (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stub and the import overlay.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers to dense fp32 (or bf16-plane, uint16_t) arrays unless noted;
+ *   - every function returns 0 on success, non-zero on error; dfold_last_error() returns the message
+ *     (thread-local, valid until the next call on that thread);
+ *   - `stream` is a cudaStream_t; work is enqueued, never synchronised;
+ *   - no function allocates device memory; workspaces are passed in by the caller.
+ */
+#ifndef DFOLD_B200_H
+#define DFOLD_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dfold_last_error(void);
+int dfold_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Split-precision tensor-core GEMM (tcgen05, bf16 x 3, fp32 accumulate in TMEM) and its operand preparation.
+ * Replaces every nn.Linear on the path (src/model/ipa_pytorch_dynamic.py:284-305,590,757-796;
+ * src/model/Dfold_network_dynamic.py:444-445; openfold/model/structure_module.py:58-59,102-110) and the
+ * ConvNet's eight Conv2d(5x5) (src/model/ipa_pytorch_dynamic.py:664-706).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* x[R,C] fp32 (row stride ld) -> bf16 planes hi = bf16(x), lo = bf16(x - hi).
+ *   hi/lo     : [R][ldo], columns [C, cpad) zero-filled           (nullable pair)
+ *   hi_t/lo_t : [C][ldt] (transposed), columns [R, rpad) zeroed   (nullable pair)
+ * pre_relu applies max(x,0) first; gate (nullable, row stride ldg) zeroes x where gate <= 0 (ReLU backward);
+ * colsum (nullable, [C], pre-zeroed) receives the column sums of the gated input (bias gradient). */
+int dfold_split2d(const float* x, long R, long C, long ld, int pre_relu, const float* gate, long ldg,
+                  uint16_t* hi, uint16_t* lo, long ldo, long cpad,
+                  uint16_t* hi_t, uint16_t* lo_t, long ldt, long rpad, float* colsum, void* stream);
+
+/* Conv weight w[O][I][T] (the reference layout [C_out, C_in, 5, 5], T = 25) ->
+ *   forward planes  f_hi/f_lo [T][O][ldi]           (K = input channel)
+ *   dgrad planes    d_hi/d_lo [T][I][ldo], tap order flipped (nullable pair) */
+int dfold_conv_weight_prep(const float* w, int O, int I, int T, uint16_t* f_hi, uint16_t* f_lo, long ldi,
+                           uint16_t* d_hi, uint16_t* d_lo, long ldo, void* stream);
+
+/* g[T][O][I] -> out[O][I][T]: weight gradient back to the parameter layout. */
+int dfold_taps_to_param(const float* g, int O, int I, int T, float* out, void* stream);
+
+/* out[f*Nr + n, c] = act(alpha * sum_{tf,tn,k} A[f + tf - taps_f/2, n + tn - taps_n/2, k] * B[tf*taps_n+tn][c][k]
+ *                        + bias[c]) + beta * residual[f*Nr + n, c]
+ * A planes [F][Nr][lda] (zero outside the image: the 5x5 halo is a TMA out-of-bounds fill), B planes
+ * [taps][n_out][ldb].  taps_f = taps_n = 1 is a plain linear layer (x @ W^T).  act: 0 none, 1 ReLU, 2 SiLU.
+ * lda, ldb multiples of 8.  bias / residual nullable. */
+int dfold_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, long F, long Nr, long K, long lda,
+                      const uint16_t* b_hi, const uint16_t* b_lo, long n_out, long ldb, int taps_f, int taps_n,
+                      float* out, long ldo, const float* bias, const float* residual, long ldr,
+                      float alpha, float beta, int act, void* stream);
+
+/* Weight gradient: out[t][m][n] = alpha * sum_{f,j} A[f][j][m] * B[f + tf - taps_f/2][j + tn - taps_n/2][n]
+ * A planes [F][Nr][lda] (gated output gradient, m = output channel), B planes [F][Nr][ldb] (layer input,
+ * n = input channel) — the same pixel-major planes as above, consumed MN-major by the tensor core; out [taps][M][ldo]. */
+int dfold_gemm_wgrad_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, long M, long lda,
+                            const uint16_t* b_hi, const uint16_t* b_lo, long Nn, long ldb,
+                            long F, long Nr, int taps_f, int taps_n,
+                            float* out, long ldo, float alpha, void* stream);
+
+/* Generic strided fp32 GEMM on CUDA cores for shapes below the tensor-core tile (K in {1,3,7,14}, N in {6,8,14}),
+ * the once-per-sample q.k logits and the reductions of the IPA backward.
+ * C[b,b2][m][n] = act(alpha * sum_k A[m][k] * B[n][k] + bias[n]) + beta * R[m][n]; strides in elements
+ * (*_rs row, *_cs column, *_bs outer batch, *_bs2 inner batch). */
+int dfold_sgemm(const float* A, long a_rs, long a_cs, long a_bs, long a_bs2,
+                const float* B, long b_rs, long b_cs, long b_bs, long b_bs2,
+                float* C, long c_rs, long c_cs, long c_bs, long c_bs2,
+                const float* R, long r_rs, long r_cs, long r_bs, long r_bs2,
+                const float* bias, int batch, int batch2, int M, int N, int K, float alpha, float beta, int act,
+                int pre_relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Norms
+ * ---------------------------------------------------------------------------------------------------------- */
+/* MyLayerNorm (src/model/ipa_pytorch_dynamic.py:709-724): y = (x - mean) / sqrt(var_unbiased + eps) with ONE
+ * mean / variance over all n elements, optional fused SiLU.  stats[2] = {mean, rstd}; workspace >= 2050 doubles. */
+int dfold_global_layernorm_fwd(const float* x, float* y, float* stats, double* workspace, long n, float eps, int silu,
+                               void* stream);
+int dfold_global_layernorm_bwd(const float* x, const float* dy, const float* stats, double* workspace, float* dx,
+                               long n, int silu, void* stream);
+/* nn.LayerNorm / openfold LayerNorm over the last axis (openfold/model/primitives.py:170-199). stats [rows][2].
+ * dw, db must be pre-zeroed. */
+int dfold_row_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, long rows, int C,
+                            float eps, void* stream);
+int dfold_row_layernorm_bwd(const float* x, const float* w, const float* dy, const float* stats, float* dx, float* dw,
+                            float* db, long rows, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Rigid-frame algebra (openfold/utils/rigid_utils.py); quaternions are (w,x,y,z), 3x3 math in registers.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* quat_to_rot :185-205 — [n,4] -> [n,3,3], not normalised. */
+int dfold_quat_to_rot_fwd(const float* quat, float* rot, long n, void* stream);
+int dfold_quat_to_rot_bwd(const float* quat, const float* drot, float* dquat, long n, void* stream);
+/* Rigid.apply :1104-1116 (inverse=0: R p + t) / Rigid.invert_apply :1118-1130 (inverse=1: R^T (p - t)).
+ * quat [F,N,4], trans [F,N,3], pts [F or 1][N][m][3] (pts_fstride = 0 shares one point set over all F), out [F,N,m,3]. */
+int dfold_rigid_apply_fwd(const float* quat, const float* trans, const float* pts, long pts_fstride, float* out,
+                          long F, long N, int m, int inverse, void* stream);
+int dfold_rigid_apply_bwd(const float* quat, const float* trans, const float* pts, long pts_fstride, const float* dout,
+                          float* dpts, float* dquat, float* dtrans, long F, long N, int m, int inverse, void* stream);
+/* Rigid.compose_q_update_vec :1039-1063 (+ :587-616, :266-275): q' = normalise(q + m q*(0,u)), t' = t + m R(q) v,
+ * upd6 = (u, v); mask [n] nullable. */
+int dfold_compose_q_update_fwd(const float* quat, const float* trans, const float* upd6, const float* mask,
+                               float* quat_out, float* trans_out, long n, void* stream);
+int dfold_compose_q_update_bwd(const float* quat, const float* upd6, const float* mask, const float* dquat_out,
+                               const float* dtrans_out, float* dquat, float* dtrans, float* dupd6, long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused invariant point attention core.
+ * Replaces src/model/ipa_pytorch_dynamic.py:402-504 (dfold=1) and openfold/model/structure_module.py:315-428
+ * (dfold=0): point-distance term on coordinate differences + pair bias + mask + softmax + value / value-point /
+ * pair aggregation + local-frame inverse transform + norms -> the concat buffer fed to linear_out.
+ *   logit0 [Fl,H,N,N]   q.k/sqrt(3C) + b/sqrt(3)        (frame stride 0 when shared by all frames)
+ *   kv     [Fs,N,H,2C]  per head [K | V]                 (frame stride 0 when shared)
+ *   q_pts  [F,N,H,Pq,3], kv_pts [F,N,H,Pq+Pv,3]          global-frame points
+ *   pair   [Fz,N,N,Cp]                                   (frame stride 0 when shared)
+ *   quat [F,N,4], trans [F,N,3], mask [F,N], gamma [H] = softplus(head_weights) * sqrt(1/(3*Pq*9/2))
+ *   out_cat [F,N,D], D = H*(C + 8*Pv + Cp) (dfold) or H*(C + 4*Pv + Cp); lse [F,H,N] (saved for backward)
+ * ---------------------------------------------------------------------------------------------------------- */
+int dfold_ipa_attn_fwd(const float* logit0, long logit0_fstride, const float* kv, long kv_fstride, const float* q_pts,
+                       const float* kv_pts, const float* pair, long pair_fstride, const float* quat, const float* trans,
+                       const float* mask, const float* gamma, int F, int N, int H, int C, int Pq, int Pv, int Cp,
+                       int dfold, float inf, float eps, float* out_cat, float* lse, void* stream);
+/* Backward: writes d_og [F,N,H,Pv,3], delta [F,H,N], P and dS [H,F,N,N] (workspaces the caller reduces into dv / dz /
+ * d-logits with dfold_sgemm), dq_pts [F,N,H,Pq,3], the key-point part of dkv_pts [F,N,H,Pq+Pv,3], dquat / dtrans of
+ * the local-frame transform, and accumulates dgamma [H] (pre-zeroed). */
+int dfold_ipa_attn_bwd(const float* logit0, long logit0_fstride, const float* kv, long kv_fstride, const float* q_pts,
+                       const float* kv_pts, const float* pair, long pair_fstride, const float* quat, const float* trans,
+                       const float* mask, const float* gamma, int F, int N, int H, int C, int Pq, int Pv, int Cp,
+                       int dfold, float inf, float eps, const float* out_cat, const float* lse, const float* dcat,
+                       float* d_og, float* delta, float* P, float* dS, float* dq_pts, float* dkv_pts, float* dquat,
+                       float* dtrans, float* dgamma, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFOLD_B200_H */

@@ -1,0 +1,132 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference (run here, where /root/reference is mounted):
+
+    python oracle/make_golden.py
+
+Each fixture stores, for one seeded case, the reference's outputs (and selected gradients); the inputs and the
+weights are NOT stored — they are regenerated from the seed by dynamicpdb_b200.synthetic (make_feats,
+random_state) in the tests, which keeps the fixtures small.  Cases cover the network (tiny / preset B / preset A
+geometry, with masked residues and a fixed residue), the vanilla OpenFold IPA and StructureModule, and the rigid
+algebra on non-unit quaternions.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shims  # noqa: E402
+
+ref_shims.install()
+from src.model import Dfold_network_dynamic as RefNet  # noqa: E402
+from src.data import se3_diffuser  # noqa: E402
+from openfold.model import structure_module as RefSM  # noqa: E402
+from openfold.utils import rigid_utils as RefRU  # noqa: E402
+from dynamicpdb_b200 import synthetic as syn  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+NET_CASES = {
+    "net_tiny": dict(preset="PRESET_TINY", nf=3, N=12, seed=3),
+    "net_B": dict(preset="PRESET_B", nf=2, N=20, seed=4),
+    "net_A": dict(preset="PRESET_A", nf=2, N=16, seed=5),
+}
+
+
+def case_feats(c):
+    feats = syn.make_feats(c["nf"], c["N"], seed=c["seed"], loader_dtypes=True)
+    feats["res_mask"][:, -2:] = 0
+    feats["fixed_mask"][:, 0] = 1
+    return feats
+
+
+def run_net(name, c):
+    preset = getattr(syn, c["preset"])
+    conf = syn.model_conf(c["nf"], **preset)
+    net = RefNet.FullScoreNetwork(conf, se3_diffuser.SE3Diffuser(syn.diffuser_conf(1.0)))
+    sd = syn.random_state({k: v.shape for k, v in net.state_dict().items()}, seed=c["seed"] + 100)
+    net.load_state_dict(sd)
+    out = net(case_feats(c))
+    loss = syn.surrogate_loss(out)
+    params = dict(net.named_parameters())
+    grads = torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+    gsel = {}
+    for (k, _), g in zip(params.items(), grads):
+        if g is None:
+            continue
+        keep = g.numel() <= 4096 or any(s in k for s in ("bb_update_3", "head_weights", "ipa_0.linear_b.weight"))
+        gsel[k] = g.detach().clone() if keep else None
+    gnorm = {k: float(g.norm()) for (k, _), g in zip(params.items(), grads) if g is not None}
+    torch.save({"case": c, "shapes": {k: tuple(v.shape) for k, v in sd.items()},
+                "out": {k: v.detach() for k, v in out.items()}, "loss": float(loss),
+                "grads": {k: v for k, v in gsel.items() if v is not None}, "grad_norms": gnorm},
+               os.path.join(OUT, name + ".pt"))
+    print(name, "loss", float(loss), "params", len(sd))
+
+
+def run_vanilla():
+    torch.manual_seed(0)
+    c_s, c_z, c_h, H, Pq, Pv, N, B = 32, 16, 8, 4, 4, 8, 14, 2
+    ipa = RefSM.InvariantPointAttention(c_s, c_z, c_h, H, Pq, Pv)
+    sd = syn.random_state({k: v.shape for k, v in ipa.state_dict().items()}, seed=21)
+    ipa.load_state_dict(sd)
+    g = torch.Generator().manual_seed(22)
+    s = torch.randn(B, N, c_s, generator=g)
+    z = torch.randn(B, N, N, c_z, generator=g)
+    rig7 = torch.cat([torch.nn.functional.normalize(torch.randn(B, N, 4, generator=g), dim=-1),
+                      torch.randn(B, N, 3, generator=g) * 5], dim=-1)
+    mask = torch.ones(B, N)
+    mask[:, -1] = 0
+    out = ipa(s, z, RefRU.Rigid.from_tensor_7(rig7), mask)
+    sm = RefSM.StructureModule(c_s=c_s, c_z=c_z, c_ipa=c_h, c_resnet=16, no_heads_ipa=H, no_qk_points=Pq, no_v_points=Pv,
+                               dropout_rate=0.0, no_blocks=2, no_transition_layers=1, no_resnet_blocks=2, no_angles=7,
+                               trans_scale_factor=10, epsilon=1e-8, inf=1e5)
+    sm.eval()
+    sd2 = syn.random_state({k: v.shape for k, v in sm.state_dict().items()}, seed=23)
+    sm.load_state_dict(sd2)
+    aatype = torch.randint(0, 20, (B, N), generator=g)
+    with torch.no_grad():
+        smo = sm({"single": s, "pair": z}, aatype, mask=mask)
+    torch.save({"ipa_shapes": {k: tuple(v.shape) for k, v in sd.items()}, "ipa_out": out.detach(),
+                "sm_shapes": {k: tuple(v.shape) for k, v in sd2.items()},
+                "sm_out": {k: v.detach() for k, v in smo.items()},
+                "dims": dict(c_s=c_s, c_z=c_z, c_h=c_h, H=H, Pq=Pq, Pv=Pv, N=N, B=B)},
+               os.path.join(OUT, "vanilla.pt"))
+    print("vanilla ok")
+
+
+def run_rigid():
+    g = torch.Generator().manual_seed(31)
+    q = torch.randn(5, 7, 4, generator=g) * 1.3          # non-unit on purpose
+    t = torch.randn(5, 7, 3, generator=g) * 4
+    pts = torch.randn(5, 7, 6, 3, generator=g) * 3
+    upd = torch.randn(5, 7, 6, generator=g) * 0.4
+    m = (torch.rand(5, 7, 1, generator=g) > 0.3).float()
+    r = RefRU.Rigid.from_tensor_7(torch.cat([q, t], -1))
+    rn = RefRU.Rigid.from_tensor_7(torch.cat([q, t], -1), normalize_quats=True)
+    out = {
+        "quat_to_rot": RefRU.quat_to_rot(q),
+        "apply": r[..., None].apply(pts),
+        "invert_apply": r[..., None].invert_apply(pts),
+        "compose_q_update": r.compose_q_update_vec(upd, m).to_tensor_7(),
+        "compose_q_update_nomask": r.compose_q_update_vec(upd).to_tensor_7(),
+        "quat_multiply": RefRU.quat_multiply(q, q.flip(0)),
+        "quat_multiply_by_vec": RefRU.quat_multiply_by_vec(q, upd[..., :3]),
+        "invert_quat": RefRU.invert_quat(q),
+        "rotvec": rn.get_rots().get_rotvec(),
+        "compose": rn.compose(RefRU.Rigid.from_tensor_7(torch.cat([q.flip(1), t.flip(1)], -1), normalize_quats=True)).to_tensor_4x4(),
+        "invert": rn.invert().to_tensor_7(),
+        "from_3_points": RefRU.Rigid.from_3_points(pts[..., 0, :], pts[..., 1, :], pts[..., 2, :]).to_tensor_4x4(),
+        "make_transform_from_reference": RefRU.Rigid.make_transform_from_reference(pts[..., 0, :], pts[..., 1, :], pts[..., 2, :]).to_tensor_4x4(),
+        "rot_to_quat_abs": RefRU.rot_to_quat(RefRU.quat_to_rot(torch.nn.functional.normalize(q, dim=-1))).abs(),
+    }
+    torch.save({k: v.detach() for k, v in out.items()}, os.path.join(OUT, "rigid.pt"))
+    print("rigid ok")
+
+
+if __name__ == "__main__":
+    for n, c in NET_CASES.items():
+        run_net(n, c)
+    run_vanilla()
+    run_rigid()

@@ -1,0 +1,180 @@
+"""-m gpu: every CUDA operator (through the C-ABI) against the plain-torch oracle, forward and backward.
+
+The oracle side runs in float64 on the CPU so the reported error is the CUDA kernel's own error.  Tolerances are
+relative to the largest reference magnitude of each tensor:
+  * fp32 CUDA-core kernels: 2e-5
+  * split-bf16 (x3) tensor-core GEMM / convolution: 1e-4 (hi/lo split keeps ~16 mantissa bits per operand)
+"""
+import math
+
+import pytest
+import torch
+
+from dynamicpdb_b200 import kernels as K
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run(fn, inputs, kwargs, dtype, device):
+    xs = []
+    for t in inputs:
+        if isinstance(t, torch.Tensor) and t.is_floating_point():
+            x = t.detach().to(device=device, dtype=dtype).requires_grad_(t.requires_grad)
+        elif isinstance(t, torch.Tensor):
+            x = t.to(device)
+        else:
+            x = t
+        xs.append(x)
+    kw = {}
+    for k, v in kwargs.items():
+        if isinstance(v, torch.Tensor) and v.is_floating_point():
+            v = v.detach().to(device=device, dtype=dtype)
+        elif isinstance(v, torch.Tensor):
+            v = v.to(device)
+        kw[k] = v
+    out = fn(*xs, **kw)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    g = torch.Generator().manual_seed(7)
+    loss = 0
+    for o in outs:
+        w = torch.randn(o.shape, generator=g).to(device=device, dtype=o.dtype)
+        loss = loss + (o * w).sum()
+    leaves = [x for x in xs if isinstance(x, torch.Tensor) and x.requires_grad]
+    grads = torch.autograd.grad(loss, leaves, allow_unused=True) if leaves else []
+    return [o.detach().double().cpu() for o in outs], [None if gr is None else gr.detach().double().cpu() for gr in grads]
+
+
+def _rel_err(a, b, outliers):
+    """max |a-b| / max|a|, ignoring the `outliers` largest deviations (ReLU gates that flip between the fp64
+    reference and the fp32 kernel when a pre-activation is within rounding of zero)."""
+    d = (a - b).abs().flatten()
+    if outliers:
+        k = min(d.numel() - 1, int(outliers))
+        d = torch.topk(d, k + 1).values[-1:]
+    return d.max().item() / (a.abs().max().item() + 1e-30)
+
+
+def check(name, inputs, tol, post=None, outliers=0, **kwargs):
+    fo = getattr(O, name) if post is None else (lambda *a, **k: post(getattr(O, name)(*a, **k), *a))
+    fk = getattr(K, name) if post is None else (lambda *a, **k: post(getattr(K, name)(*a, **k), *a))
+    ro, rg = _run(fo, inputs, kwargs, torch.float64, "cpu")
+    co, cg = _run(fk, inputs, kwargs, torch.float32, DEV)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(ro, co)):
+        assert a.shape == b.shape, f"{name} out{i} shape {a.shape} vs {b.shape}"
+        err = _rel_err(a, b, 0)
+        assert err < tol, f"{name} out{i}: rel err {err:.3e} >= {tol}"
+    for i, (a, b) in enumerate(zip(rg, cg)):
+        assert (a is None) == (b is None), f"{name} grad{i} presence"
+        if a is None:
+            continue
+        assert a.shape == b.shape, f"{name} grad{i} shape {a.shape} vs {b.shape}"
+        err = _rel_err(a, b, outliers)
+        assert err < tol, f"{name} grad{i}: rel err {err:.3e} >= {tol}"
+
+
+def R(*s, grad=True, scale=1.0, seed=None):
+    g = torch.Generator().manual_seed(seed if seed is not None else (hash(s) % 1000))
+    return (torch.randn(*s, generator=g) * scale).requires_grad_(grad)
+
+
+def unit(*s, grad=True):
+    q = R(*s, grad=False)
+    return (q / q.norm(dim=-1, keepdim=True)).requires_grad_(grad)
+
+
+def test_library_loads():
+    assert K.lib().dfold_abi_version() == 1
+
+
+@pytest.mark.parametrize("M,Kd,N", [(5, 3, 16), (70, 14, 32), (33, 7, 6), (256, 160, 6), (100, 128, 8)])
+@pytest.mark.parametrize("act,pre_relu,res", [(None, False, False), ("relu", False, False), (None, True, True), ("silu", False, False)])
+def test_linear_simt(M, Kd, N, act, pre_relu, res):
+    inputs = [R(M, Kd), R(N, Kd, scale=0.3), R(N)]
+    check("linear", inputs, 2e-5, act=act, pre_relu=pre_relu, residual=R(M, N) if res else None)
+
+
+@pytest.mark.parametrize("M,Kd,N", [(128, 64, 64), (256, 256, 2048), (300, 1280, 640), (130, 3072, 256), (4096, 128, 32), (512, 160, 80)])
+@pytest.mark.parametrize("act,pre_relu,res", [(None, False, False), ("relu", False, True), (None, True, True)])
+def test_linear_tensor_core(M, Kd, N, act, pre_relu, res):
+    inputs = [R(M, Kd), R(N, Kd, scale=1.0 / math.sqrt(Kd)), R(N)]
+    # a ReLU whose pre-activation is within fp32 rounding of 0 may gate differently than the fp64 reference: allow
+    # that many isolated rows/columns of the gradients to deviate
+    check("linear", inputs, 1e-4, outliers=(6 * max(M, Kd, N) if (act or pre_relu) else 0), act=act, pre_relu=pre_relu,
+          residual=R(M, N) if res else None)
+
+
+@pytest.mark.parametrize("F,N,Ci,Co", [(2, 16, 160, 80), (3, 12, 80, 160), (5, 130, 64, 128), (8, 256, 320, 256), (1, 40, 256, 640)])
+@pytest.mark.parametrize("relu,res", [(True, False), (True, True), (False, False)])
+def test_conv5x5(F, N, Ci, Co, relu, res):
+    inputs = [R(F, N, Ci), R(Co, Ci, 5, 5, scale=1.0 / math.sqrt(25 * Ci)), R(Co)]
+    residual = R(F, N, Co) if res else None
+    check("conv5x5", inputs, 1e-4, outliers=(60 * max(Ci, Co) if relu else 0), relu=relu, residual=residual)
+
+
+@pytest.mark.parametrize("shape", [(3, 12, 32), (8, 256, 256), (1, 7, 5)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_global_layernorm(shape, silu):
+    check("global_layernorm", [R(*shape, scale=3.0) + 0.7], 2e-5, eps=1e-4, silu=silu)
+
+
+def test_row_layernorm():
+    check("layer_norm", [R(37, 96), R(96), R(96)], 2e-5, eps=1e-5)
+
+
+def test_quat_to_rot():
+    check("quat_to_rot", [R(4, 33, 4)], 2e-5)     # deliberately non-unit
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_rigid_apply(inverse):
+    q, t = R(3, 20, 1, 4), R(3, 20, 1, 3, scale=10.0)
+    check("rigid_apply", [q, t, R(3, 20, 17, 3, scale=5.0)], 2e-5, inverse=inverse)
+    check("rigid_apply", [R(6, 4), R(6, 3), R(6, 3)], 2e-5, inverse=inverse)
+
+
+@pytest.mark.parametrize("Fs", [1, 3])
+def test_ipa_points(Fs):
+    check("ipa_points", [R(Fs, 20, 3 * 4 * 5), unit(3, 20, 4), R(3, 20, 3, scale=10.0), 4], 2e-5)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_compose_q_update(masked):
+    m = None
+    if masked:
+        m = (torch.rand(3, 20, 1) > 0.3).float()
+    check("compose_q_update", [unit(3, 20, 4), R(3, 20, 3, scale=10.0), R(3, 20, 6, scale=0.3), m], 2e-5)
+
+
+@pytest.mark.parametrize("Fs,Fz", [(1, 1), (2, 1), (2, 2)])
+def test_qk_logits(Fs, Fz):
+    N, H, C = 24, 3, 16
+    b = R(Fz, N, N, H).permute(0, 3, 1, 2)       # head-major view, as the module produces it
+    check("qk_logits", [R(Fs, N, H, C), R(Fs, N, H, 2 * C), b.detach().requires_grad_(True), 0.25, 0.577], 2e-5)
+
+
+def _ipa_inputs(F, N, H, C, Pq, Pv, Cp, Fs, Fz, masked):
+    mask = torch.ones(F, N)
+    if masked:
+        mask[:, -3:] = 0
+        mask[0, 1] = 0
+    return [R(max(Fs, Fz), H, N, N), R(Fs, N, H, 2 * C), R(F, N, H, Pq, 3, scale=4.0), R(F, N, H, Pq + Pv, 3, scale=4.0),
+            R(Fz, N, N, Cp), unit(F, N, 4), R(F, N, 3, scale=8.0), mask, (torch.rand(H) * 0.2 + 0.05).requires_grad_(True)]
+
+
+@pytest.mark.parametrize("F,N,H,C,Pq,Pv,Cp,Fs,Fz,dfold", [
+    (3, 12, 2, 8, 2, 3, 4, 1, 1, True),        # tiny preset
+    (2, 20, 12, 16, 4, 8, 32, 1, 1, True),     # preset B
+    (2, 40, 8, 256, 8, 12, 32, 1, 1, True),    # preset A geometry
+    (2, 33, 4, 16, 4, 8, 64, 2, 2, False),     # vanilla OpenFold, batched z and per-frame s
+    (3, 70, 2, 8, 2, 3, 4, 3, 1, True),        # per-frame s, shared z, N not a multiple of the tiles
+])
+@pytest.mark.parametrize("masked", [False, True])
+def test_ipa_attention(F, N, H, C, Pq, Pv, Cp, Fs, Fz, dfold, masked):
+    inputs = _ipa_inputs(F, N, H, C, Pq, Pv, Cp, Fs, Fz, masked)
+    # rows of masked QUERY residues see every logit shifted by -1e5: in fp32 (reference and kernel alike) that
+    # quantises the logits to 2^-7, so those rows are compared only through the unmasked ones
+    post = lambda out, *a: out * a[7][:, :, None]
+    check("ipa_attention", inputs, 2e-4, post=post, Pq=Pq, Pv=Pv, dfold=dfold, inf=1e5, eps=1e-8)
