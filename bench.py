@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the DFOLDv2 score-network training step (BASELINE.json metric: frames/s, fwd+bwd, N_res=256,
+64 trajectory frames per sample), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --steps K --warmup W    # the CPU oracle port, timed on the host cores
+
+A step = zero_grad + forward + surrogate loss + backward (+ NCCL gradient all-reduce through DDP when N > 1)
++ Adam(amsgrad) step on ONE protein window of `--frames` frames x `--res` residues per rank (the only shape the
+reference executes in one forward).  Weak scaling: every rank processes its own window.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "DFOLDv2 frames/sec (fwd+bwd, N_res=256, batch=64)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames in the bounded CPU sample")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU oracle (reference arm / cpu_baseline)
+# --------------------------------------------------------------------------------------------------
+def cpu_oracle_fps(frames, n_res, steps, warmup):
+    """frames/s of the CPU restatement (oracle/dfold_oracle.py) on the host cores: forward + backward of one window of
+    `frames` frames x `n_res` residues, all torch intra-op threads."""
+    from dynamicpdb_b200 import synthetic as syn
+    from oracle import dfold_oracle as O
+    torch.manual_seed(0)
+    conf = syn.model_conf(frames, **syn.PRESET_A)
+    from dynamicpdb_b200.Dfold_network_dynamic import FullScoreNetwork
+    from dynamicpdb_b200.score_epilogue import SE3ScoreDiffuser
+    net = FullScoreNetwork(conf, SE3ScoreDiffuser(syn.diffuser_conf(1.0)))      # only used to draw the weights
+    sd = net.state_dict()
+    syn.dezero_(sd)
+    p = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in sd.items()}
+    del net
+    feats = syn.make_feats(frames, n_res, seed=0)
+    oc, dc = O.default_conf(**syn.PRESET_A), O.default_diffuser_conf(1.0)
+    leaves = [v for v in p.values() if v.requires_grad]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.full_forward(p, feats, oc, dc)
+        loss = O.surrogate_loss(out)
+        torch.autograd.grad(loss, leaves, allow_unused=True)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return frames / (ms / 1e3), ms
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    frames = args.cpu_frames
+    fps, ms = cpu_oracle_fps(frames, args.res, args.steps, args.warmup)
+    sample = f"one window of {frames} frames x {args.res} residues per step (per-frame cost is linear in the frame count)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DFOLDv2 training step fwd+bwd, N_res={args.res}, CPU oracle port (bounded sample)",
+                   "frames_per_step": frames, "n_res": args.res, "preset": "train_DFOLDv2.yaml"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# the CUDA path
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from dynamicpdb_b200 import kernels as K
+    from dynamicpdb_b200 import synthetic as syn
+    from dynamicpdb_b200.Dfold_network_dynamic import FullScoreNetwork
+    from dynamicpdb_b200.score_epilogue import SE3ScoreDiffuser
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K.lib()
+
+    nf, N = args.frames, args.res
+    torch.manual_seed(0)
+    conf = syn.model_conf(nf, **syn.PRESET_A)
+    net = FullScoreNetwork(conf, SE3ScoreDiffuser(syn.diffuser_conf(1.0)))
+    sd = net.state_dict()
+    syn.dezero_(sd)
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True,
+                                                          gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, amsgrad=True)    # train_DFOLD_dynamics.py:412
+
+    host = syn.make_feats(nf, N, seed=rank)                             # one protein window per rank
+    host = {k: v.pin_memory() for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    resident = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step(feats):
+        opt.zero_grad(set_to_none=True)
+        out = model(dict(feats))
+        loss = syn.surrogate_loss(out)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            if e2e:
+                feats = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+                loss = step(feats)
+                loss_host.copy_(loss.detach().float(), non_blocking=True)
+            else:
+                step(resident)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step(resident)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    K.LAUNCH_COUNT = 0
+    K.PROFILE = [] if rank == 0 else None
+    ms = timed(args.steps, e2e=False)
+    launches = K.LAUNCH_COUNT // max(1, args.steps)
+    prof, K.PROFILE = K.PROFILE, None
+    ms_e2e = timed(args.steps, e2e=True)
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the split-bf16 tensor-core GEMM) and of the fused IPA forward ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak, tf_src = (peaks.get("bf16_tflops_sustained"), "measured (sustained)") if peaks.get("bf16_tflops_sustained") \
+        else (1400.0, "fallback")
+    hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    agg = {}
+    for name, work, a, b in prof:
+        t = a.elapsed_time(b) * 1e-3
+        d = agg.setdefault(name, [0.0, 0.0, 0])
+        d[0] += work
+        d[1] += t
+        d[2] += 1
+    roof = None
+    if "gemm_bf16x3" in agg:
+        w, t, n = agg["gemm_bf16x3"]
+        ach = w / t / 1e12
+        roof = {"kernel": "gemm_bf16x3_kernel (implicit 5x5 conv / linear, 3 bf16 MMAs per fp32 product)",
+                "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                "peak_source": tf_src, "traffic": None, "launches_timed": n, "avg_launch_ms": 1e3 * t / n,
+                "share_of_step": (t / args.steps) / (ms * 1e-3), "tensor_pipe_frac": 3 * ach / tf_peak,
+                "note": "achieved counts fp32-equivalent FLOPs; the split issues 3 bf16 MMAs per product, so frac <= 1/3"}
+    roof_ipa = None
+    if "ipa_fwd" in agg:
+        w, t, n = agg["ipa_fwd"]
+        ach = w / t / 1e9
+        roof_ipa = {"kernel": "ipa_fwd_kernel (fused IPA core)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src, "traffic": None,
+                    "launches_timed": n, "avg_launch_ms": 1e3 * t / n, "share_of_step": (t / args.steps) / (ms * 1e-3),
+                    "note": "algorithmic bytes per SURVEY.md 8(d) (per-frame q/k/v formulation)"}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = torch.get_num_threads()
+        fps, cms = cpu_oracle_fps(args.cpu_frames, N, 1, 1)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"one fwd+bwd of {args.cpu_frames} frames x {N} residues ({cms / 1e3:.1f} s), oracle/dfold_oracle.py"}
+
+    line = {
+        "metric": METRIC, "value": world * nf / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"DFOLDv2 training step fwd+bwd+Adam, N_res={N}, batch={nf} frames per rank (configs[2])",
+                   "frames_per_rank": nf, "n_res": N, "preset": "train_DFOLDv2.yaml (c_s 256, c_z 128, C 256, H 8, Pq 8, Pv 12, 4 blocks)",
+                   "parallelism": f"dp{world}", "l2": "working set (weights 738 MB + activations) exceeds the 126 MB L2"},
+        "e2e": {"value": world * nf / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_ipa": roof_ipa, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -68,9 +68,38 @@ def exported_symbols():
     return sorted(list(_SIGS) + ["dfold_last_error"])
 
 
+# kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
+_LAUNCHES_PER_CALL = {"dfold_global_layernorm_fwd": 3, "dfold_global_layernorm_bwd": 3, "dfold_ipa_attn_bwd": 4}
+LAUNCH_COUNT = 0
+# optional per-launch timing: when PROFILE is a list, timed(...) appends (name, work, start_event, end_event)
+PROFILE = None
+
+
 def _check(rc: int, what: str):
+    global LAUNCH_COUNT
     if rc != 0:
         raise RuntimeError(f"{what}: {lib().dfold_last_error().decode()}")
+    LAUNCH_COUNT += _LAUNCHES_PER_CALL.get(what, 1)
+
+
+class _timed:
+    """Brackets one kernel launch with CUDA events on the launching stream when profiling is enabled."""
+
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            PROFILE.append((self.name, self.work, self.e0, self.e1))
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor], offset: int = 0):
@@ -179,12 +208,22 @@ def _conv_planes(w: torch.Tensor):
 
 
 def _gemm(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act):
+    with _timed("gemm_bf16x3", 2.0 * F * Nr * K * n_out * taps_f * taps_n):
+        _gemm_launch(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act)
+
+
+def _gemm_launch(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act):
     _check(lib().dfold_gemm_bf16x3(_ptr(a_hi), _ptr(a_lo), F, Nr, K, lda, _ptr(b_hi), _ptr(b_lo), n_out, ldb, taps_f, taps_n,
                                    _ptr(out), ldo, _ptr(bias), _ptr(residual), ldr, alpha, beta, act, _stream()),
            "dfold_gemm_bf16x3")
 
 
 def _gemm_wgrad(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo):
+    with _timed("gemm_bf16x3", 2.0 * F * Nr * M * Nn * taps_f * taps_n):
+        _gemm_wgrad_launch(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo)
+
+
+def _gemm_wgrad_launch(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo):
     _check(lib().dfold_gemm_wgrad_bf16x3(_ptr(a[0]), _ptr(a[1]), M, lda, _ptr(b[0]), _ptr(b[1]), Nn, ldb, F, Nr, taps_f, taps_n,
                                          _ptr(out), ldo, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3")
 
@@ -601,7 +640,11 @@ class _IpaAttnFn(Function):
         cat = torch.empty((F_, N_, D), dtype=torch.float32, device=q_pts.device)
         lse = torch.empty((F_, H_, N_), dtype=torch.float32, device=q_pts.device)
         args = _IpaAttnFn._args(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
-        _check(lib().dfold_ipa_attn_fwd(*args, _ptr(cat), _ptr(lse), _stream()), "dfold_ipa_attn_fwd")
+        # algorithmic fp32 bytes of the fused core: per-frame q/k/v/points/rigids/mask in, concat out,
+        # plus the per-sample pair bias and pair values
+        alg_bytes = 4.0 * (F_ * N_ * (H_ * (4 * C_ + 3 * (2 * Pq + Pv) + 8 * Pv + Cp) + 8) + N_ * N_ * (H_ + Cp))
+        with _timed("ipa_fwd", alg_bytes):
+            _check(lib().dfold_ipa_attn_fwd(*args, _ptr(cat), _ptr(lse), _stream()), "dfold_ipa_attn_fwd")
         ctx.save_for_backward(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, cat, lse)
         ctx.meta = (Pq, Pv, dfold, inf, eps)
         return cat
