@@ -56,6 +56,23 @@ struct GemmParams {
     const float* res; long ldr;
     float alpha, beta;
     int act;             // 0 none, 1 relu, 2 silu
+    // ---- batching (defaults describe the plain conv / linear case) ----
+    // mode 0: the "frame" index f0 of a row tile doubles as a batch id: hb = f0 % bmod
+    int bmod;            // >= 1
+    int a_f_div;         // A frame coordinate            = f0 / a_f_div
+    int a_k_bstride;     // A K-coordinate offset         = hb * a_k_bstride
+    int b_k_ofs;         // B K-coordinate offset         = b_k_ofs + hb * b_k_bstride
+    int b_k_bstride;
+    int b_z_bstride;     // B third coordinate            = tap + hb * b_z_bstride
+    int o_f_div;         // output row                    = (f0 / o_f_div) * Nr + n
+    long o_col_bstride;  // output column offset          = hb * o_col_bstride
+    // mode 1: blockIdx.z = zq * zdiv + zs  (zq: tap or batch id, zs: K split)
+    int zdiv;
+    int a_f_mul, a_z_mul;   // A outer coordinate = f * a_f_mul + zq * a_z_mul
+    int b_f_mul, b_z_mul;   // B outer coordinate = f * b_f_mul + zq * b_z_mul (+ df)
+    int b_n_zmul;           // B column offset    = zq * b_n_zmul
+    int kb_per_split;       // k-blocks per K split
+    int atomic;             // epilogue accumulates with atomicAdd (split-K)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -160,13 +177,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     // ---- tile coordinates ----
     const int n_tile = blockIdx.x;                 // output column tile
     const int m_tile = blockIdx.y;
-    const int tap_z = blockIdx.z;                  // mode 1 only
-    int f0 = 0, n0 = 0, m0 = 0;
+    const int zq = (p.mode == 1) ? (int)blockIdx.z / p.zdiv : 0;     // mode 1: tap or batch id
+    const int zs = (p.mode == 1) ? (int)blockIdx.z % p.zdiv : 0;     // mode 1: K split
+    int f0 = 0, n0 = 0, m0 = 0, hb = 0;
+    int kb_begin = 0, num_kb = p.num_kb;
     if (p.mode == 0) {
         f0 = m_tile / p.tiles_per_frame;
         n0 = (m_tile % p.tiles_per_frame) * BM;
+        hb = f0 % p.bmod;
     } else {
         m0 = m_tile * BM;
+        kb_begin = zs * p.kb_per_split;
+        num_kb = min(p.kb_per_split, p.num_kb - kb_begin);
     }
     const int col0 = n_tile * BN;
 
@@ -188,7 +210,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (warp == 0) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % Cfg::kStages;
                 const uint32_t ph = (kb / Cfg::kStages) & 1;
                 mbar_wait(empty_bar(s), ph ^ 1u);
@@ -201,26 +223,35 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const int tap = kb / p.kc, c = kb % p.kc;
                     const int dn = tap % p.taps_n - p.taps_n / 2;
                     const int df = tap / p.taps_n - p.taps_f / 2;
-                    tma_load_3d(sa_hi, &map_a_hi, full_bar(s), c * BK, n0 + dn, f0 + df);
-                    tma_load_3d(sa_lo, &map_a_lo, full_bar(s), c * BK, n0 + dn, f0 + df);
-                    tma_load_3d(sb_hi, &map_b_hi, full_bar(s), c * BK, col0, tap);
-                    tma_load_3d(sb_lo, &map_b_lo, full_bar(s), c * BK, col0, tap);
+                    const int ak = c * BK + hb * p.a_k_bstride;
+                    const int af = f0 / p.a_f_div + df;
+                    const int bk = c * BK + p.b_k_ofs + hb * p.b_k_bstride;
+                    const int bz = tap + hb * p.b_z_bstride;
+                    tma_load_3d(sa_hi, &map_a_hi, full_bar(s), ak, n0 + dn, af);
+                    tma_load_3d(sa_lo, &map_a_lo, full_bar(s), ak, n0 + dn, af);
+                    tma_load_3d(sb_hi, &map_b_hi, full_bar(s), bk, col0, bz);
+                    tma_load_3d(sb_lo, &map_b_lo, full_bar(s), bk, col0, bz);
                 } else {
                     // K runs over pixels (f, 64-residue block j); operands are MN-major: boxes of
                     // 64 channels x 64 residues, one per 64-wide channel atom.  The tap shift is on the
                     // residue / frame coordinates (row dimensions), out-of-image rows are zero-filled.
-                    const int f = kb / p.kc, j = kb % p.kc;
-                    const int dn = tap_z % p.taps_n - p.taps_n / 2;
-                    const int df = tap_z / p.taps_n - p.taps_f / 2;
+                    const int kg = kb_begin + kb;
+                    const int f = kg / p.kc, j = kg % p.kc;
+                    const bool has_taps = p.taps_n * p.taps_f > 1;
+                    const int dn = has_taps ? zq % p.taps_n - p.taps_n / 2 : 0;
+                    const int df = has_taps ? zq / p.taps_n - p.taps_f / 2 : 0;
+                    const int af = f * p.a_f_mul + zq * p.a_z_mul;
+                    const int bf = f * p.b_f_mul + zq * p.b_z_mul + df;
+                    const int bn0 = col0 + zq * p.b_n_zmul;
 #pragma unroll
                     for (int a = 0; a < BM / 64; ++a) {
-                        tma_load_3d(sa_hi + a * 8192, &map_a_hi, full_bar(s), m0 + a * 64, j * BK, f);
-                        tma_load_3d(sa_lo + a * 8192, &map_a_lo, full_bar(s), m0 + a * 64, j * BK, f);
+                        tma_load_3d(sa_hi + a * 8192, &map_a_hi, full_bar(s), m0 + a * 64, j * BK, af);
+                        tma_load_3d(sa_lo + a * 8192, &map_a_lo, full_bar(s), m0 + a * 64, j * BK, af);
                     }
 #pragma unroll
                     for (int b = 0; b < BN / 64; ++b) {
-                        tma_load_3d(sb_hi + b * 8192, &map_b_hi, full_bar(s), col0 + b * 64, j * BK + dn, f + df);
-                        tma_load_3d(sb_lo + b * 8192, &map_b_lo, full_bar(s), col0 + b * 64, j * BK + dn, f + df);
+                        tma_load_3d(sb_hi + b * 8192, &map_b_hi, full_bar(s), bn0 + b * 64, j * BK + dn, bf);
+                        tma_load_3d(sb_lo + b * 8192, &map_b_lo, full_bar(s), bn0 + b * 64, j * BK + dn, bf);
                     }
                 }
             }
@@ -232,7 +263,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const bool mn_major = (p.mode == 1);
             if (mn_major) idesc |= (1u << 15) | (1u << 16);     // A and B are MN-major in weight-gradient mode
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % Cfg::kStages;
                 const uint32_t ph = (kb / Cfg::kStages) & 1;
                 const int chunk = kb / kChunk;
@@ -264,7 +295,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     umma_bf16(tmem_d, da_hi + koff, db_hi + koff, idesc, 1u);
                 }
                 umma_commit(empty_bar(s));      // smem stage reusable once these MMAs retire
-                if ((kb % kChunk) == kChunk - 1 || kb == p.num_kb - 1)
+                if ((kb % kChunk) == kChunk - 1 || kb == num_kb - 1)
                     umma_commit(acc_full_bar(buf));   // this chunk's partial sum is complete
             }
         }
@@ -276,7 +307,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         float acc[HALF];
 #pragma unroll
         for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
-        const int nchunks = (p.num_kb + kChunk - 1) / kChunk;
+        const int nchunks = (num_kb + kChunk - 1) / kChunk;
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             const int buf = chunk & 1;
             mbar_wait(acc_full_bar(buf), (chunk >> 1) & 1);
@@ -297,16 +328,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         bool row_ok;
         if (p.mode == 0) {
             const int n = n0 + r;
-            row_ok = (n < p.Nr) && ((long)f0 * p.Nr + n < p.out_rows);
-            grow = (long)f0 * p.Nr + n;
+            grow = (long)(f0 / p.o_f_div) * p.Nr + n;
+            row_ok = (n < p.Nr) && (grow < p.out_rows);
         } else {
             grow = m0 + r;
             row_ok = grow < p.out_rows;
         }
-        float* orow = p.out + (p.mode == 1 ? (long)tap_z * p.out_tap_stride : 0) + grow * p.ldo;
-        const float* rrow = p.res ? p.res + grow * p.ldr : nullptr;
-        const bool vec_ok = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
-                            (p.out_tap_stride % 4 == 0);
+        const long obase = (p.mode == 1 ? (long)zq * p.out_tap_stride : (long)hb * p.o_col_bstride);
+        float* orow = p.out + obase + grow * p.ldo;
+        const float* rrow = p.res ? p.res + (p.mode == 0 ? (long)hb * p.o_col_bstride : 0) + grow * p.ldr : nullptr;
+        const bool vec_ok = !p.atomic && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                            (p.out_tap_stride % 4 == 0) && (p.o_col_bstride % 4 == 0);
         if (row_ok) {
 #pragma unroll
             for (int c0 = 0; c0 < HALF; c0 += 4) {
@@ -327,6 +359,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 }
                 if (vec_ok && gc0 + 4 <= p.n_out) {
                     *reinterpret_cast<float4*>(orow + gc0) = make_float4(o[0], o[1], o[2], o[3]);
+                } else if (p.atomic) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gc0 + i < p.n_out) atomicAdd(orow + gc0 + i, o[i]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -392,6 +428,13 @@ int launch(const CUtensorMap* maps, const GemmParams& p, dim3 grid, cudaStream_t
     return check_launch("gemm_bf16x3_kernel");
 }
 
+void default_batching(GemmParams& p) {
+    p.bmod = 1; p.a_f_div = 1; p.a_k_bstride = 0; p.b_k_ofs = 0; p.b_k_bstride = 0; p.b_z_bstride = 0;
+    p.o_f_div = 1; p.o_col_bstride = 0;
+    p.zdiv = 1; p.a_f_mul = 1; p.a_z_mul = 0; p.b_f_mul = 1; p.b_z_mul = 0; p.b_n_zmul = 0;
+    p.kb_per_split = p.num_kb; p.atomic = 0;
+}
+
 int pick_bn(long n_out) {
     if (n_out % 256 == 0 || n_out > 640) return 256;
     if (n_out > 64) return 128;
@@ -434,6 +477,7 @@ extern "C" int dfold_gemm_bf16x3(
     p.out = out; p.ldo = ldo; p.out_tap_stride = 0;
     p.bias = bias; p.res = residual; p.ldr = ldr;
     p.alpha = alpha; p.beta = beta; p.act = act;
+    default_batching(p);
     dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(F * p.tiles_per_frame), 1);
     cudaStream_t st = as_stream(stream);
     if (bn == 256) return launch<256>(maps, p, grid, st);
@@ -468,7 +512,94 @@ extern "C" int dfold_gemm_wgrad_bf16x3(
     p.out = out; p.ldo = ldo; p.out_tap_stride = M * ldo;
     p.bias = nullptr; p.res = nullptr; p.ldr = 0;
     p.alpha = alpha; p.beta = 0.f; p.act = 0;
+    default_batching(p);
     dim3 grid((unsigned)cdiv(Nn, bn), (unsigned)cdiv(M, BM), (unsigned)(taps_f * taps_n));
+    cudaStream_t st = as_stream(stream);
+    if (bn == 256) return launch<256>(maps, p, grid, st);
+    if (bn == 128) return launch<128>(maps, p, grid, st);
+    return launch<64>(maps, p, grid, st);
+}
+
+// Batched K-major GEMM (no taps): for every row tile of "frame" b in [0, n_batches), hb = b % bmod:
+//   out[(b / o_f_div) * Nr + n, hb * o_col_bstride + c] = alpha * sum_k A[b / a_f_div][n][hb * a_k_bstride + k]
+//                                                                    * B[hb * b_z_bstride][c][b_k_ofs + hb * b_k_bstride + k]
+// A planes: [a_frames][Nr][lda]; B planes: [b_z][b_rows][ldb].
+extern "C" int dfold_gemm_bf16x3_batched(
+    const uint16_t* a_hi, const uint16_t* a_lo, long a_frames, long Nr, long a_cols, long lda,
+    long n_batches, int bmod, int a_f_div, long a_k_bstride, long K,
+    const uint16_t* b_hi, const uint16_t* b_lo, long b_z, long b_rows, long b_cols, long ldb,
+    long b_k_ofs, long b_k_bstride, int b_z_bstride, long n_out,
+    float* out, long ldo, long out_rows, int o_f_div, long o_col_bstride, float alpha, void* stream) {
+    DFOLD_REQUIRE(n_batches > 0 && Nr > 0 && K > 0 && n_out > 0 && bmod >= 1, "dfold_gemm_bf16x3_batched: empty problem");
+    DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dfold_gemm_bf16x3_batched: lda/ldb must be multiples of 8");
+    DFOLD_REQUIRE(a_k_bstride % 8 == 0 && b_k_ofs % 8 == 0 && b_k_bstride % 8 == 0,
+                  "dfold_gemm_bf16x3_batched: K offsets must be multiples of 8 elements (TMA 16-byte alignment)");
+    const int bn = pick_bn(n_out);
+    CUtensorMap maps[4];
+    if (make_map(&maps[0], a_hi, a_cols, Nr, a_frames, lda, Nr * lda, BK, BM, 1)) return 1;
+    if (make_map(&maps[1], a_lo, a_cols, Nr, a_frames, lda, Nr * lda, BK, BM, 1)) return 1;
+    if (make_map(&maps[2], b_hi, b_cols, b_rows, b_z, ldb, b_rows * ldb, BK, bn, 1)) return 1;
+    if (make_map(&maps[3], b_lo, b_cols, b_rows, b_z, ldb, b_rows * ldb, BK, bn, 1)) return 1;
+    GemmParams p{};
+    p.mode = 0;
+    p.kc = (int)cdiv(K, BK);
+    p.num_kb = p.kc;
+    p.taps_n = 1; p.taps_f = 1;
+    p.tiles_per_frame = (int)cdiv(Nr, BM);
+    p.Nr = (int)Nr;
+    p.out_rows = out_rows;
+    p.n_out = (int)n_out;
+    p.out = out; p.ldo = ldo; p.out_tap_stride = 0;
+    p.bias = nullptr; p.res = nullptr; p.ldr = 0;
+    p.alpha = alpha; p.beta = 0.f; p.act = 0;
+    default_batching(p);
+    p.bmod = bmod; p.a_f_div = a_f_div; p.a_k_bstride = (int)a_k_bstride;
+    p.b_k_ofs = (int)b_k_ofs; p.b_k_bstride = (int)b_k_bstride; p.b_z_bstride = b_z_bstride;
+    p.o_f_div = o_f_div; p.o_col_bstride = o_col_bstride;
+    // K tail: the A / B boxes may run past [k_ofs, k_ofs + K) into the neighbouring batch slice; require K % 64 == 0
+    DFOLD_REQUIRE(K % BK == 0 || (a_k_bstride == 0 && b_k_ofs == 0 && b_k_bstride == 0),
+                  "dfold_gemm_bf16x3_batched: K must be a multiple of 64 when it is a slice of a wider row");
+    dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(n_batches * p.tiles_per_frame), 1);
+    cudaStream_t st = as_stream(stream);
+    if (bn == 256) return launch<256>(maps, p, grid, st);
+    if (bn == 128) return launch<128>(maps, p, grid, st);
+    return launch<64>(maps, p, grid, st);
+}
+
+// Batched / split-K MN-major GEMM (K = rows):  for z = zq * splits + zs
+//   out[zq][m][n] (+)= alpha * sum_{f in split zs} sum_j A[f * a_f_mul + zq * a_z_mul][j][m] * B[f * b_f_mul + zq * b_z_mul][j][zq * b_n_zmul + n]
+// A planes: dims (M, a_mid, a_outer) with element strides (lda, a_ostride); B likewise.  K loop: Fk outer x ceil(Nr/64) blocks.
+extern "C" int dfold_gemm_wgrad_bf16x3_batched(
+    const uint16_t* a_hi, const uint16_t* a_lo, long M, long a_mid, long a_outer, long lda, long a_ostride,
+    const uint16_t* b_hi, const uint16_t* b_lo, long b_cols, long b_mid, long b_outer, long ldb, long b_ostride,
+    long Nn, long Fk, long Nr, int zcount, int splits, int a_f_mul, int a_z_mul, int b_f_mul, int b_z_mul, long b_n_zmul,
+    float* out, long ldo, long out_z_stride, float alpha, void* stream) {
+    DFOLD_REQUIRE(M > 0 && Nn > 0 && Fk > 0 && Nr > 0 && zcount > 0 && splits > 0, "dfold_gemm_wgrad_bf16x3_batched: empty problem");
+    DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_ostride % 8 == 0 && b_ostride % 8 == 0 && b_n_zmul % 8 == 0,
+                  "dfold_gemm_wgrad_bf16x3_batched: strides / offsets must be multiples of 8 elements");
+    const int bn = pick_bn(Nn);
+    CUtensorMap maps[4];
+    if (make_map(&maps[0], a_hi, M, a_mid, a_outer, lda, a_ostride, 64, BK, 1)) return 1;
+    if (make_map(&maps[1], a_lo, M, a_mid, a_outer, lda, a_ostride, 64, BK, 1)) return 1;
+    if (make_map(&maps[2], b_hi, b_cols, b_mid, b_outer, ldb, b_ostride, 64, BK, 1)) return 1;
+    if (make_map(&maps[3], b_lo, b_cols, b_mid, b_outer, ldb, b_ostride, 64, BK, 1)) return 1;
+    GemmParams p{};
+    p.mode = 1;
+    p.kc = (int)cdiv(Nr, BK);
+    p.num_kb = (int)(Fk * p.kc);
+    p.taps_n = 1; p.taps_f = 1;
+    p.tiles_per_frame = 1; p.Nr = (int)Nr;
+    p.out_rows = M; p.n_out = (int)Nn;
+    p.out = out; p.ldo = ldo; p.out_tap_stride = out_z_stride;
+    p.bias = nullptr; p.res = nullptr; p.ldr = 0;
+    p.alpha = alpha; p.beta = 0.f; p.act = 0;
+    default_batching(p);
+    p.zdiv = splits;
+    p.a_f_mul = a_f_mul; p.a_z_mul = a_z_mul; p.b_f_mul = b_f_mul; p.b_z_mul = b_z_mul; p.b_n_zmul = (int)b_n_zmul;
+    p.kb_per_split = (int)cdiv(p.num_kb, splits);
+    p.atomic = splits > 1;
+    DFOLD_REQUIRE((long)zcount * splits <= 65535, "dfold_gemm_wgrad_bf16x3_batched: too many z blocks");
+    dim3 grid((unsigned)cdiv(Nn, bn), (unsigned)cdiv(M, BM), (unsigned)(zcount * splits));
     cudaStream_t st = as_stream(stream);
     if (bn == 256) return launch<256>(maps, p, grid, st);
     if (bn == 128) return launch<128>(maps, p, grid, st);

@@ -549,3 +549,15 @@ extern "C" int dfold_ipa_attn_bwd(IPA_ARGS, const float* out_cat, const float* l
     }
     return check_launch("ipa_bwd_pts_kernel");
 }
+
+// Epilogue-only backward (used by the tensor-core decomposition, csrc/ipa_v2.cu): d_og [F,N,H,Pv,3], delta [F,H,N],
+// dquat [F,N,4], dtrans [F,N,3] from the concat buffer and its gradient.
+extern "C" int dfold_ipa_pre_bwd(const float* quat, const float* trans, int F, int N, int H, int C, int Pv, int Cp, int dfold,
+                                 const float* out_cat, const float* dcat, float* d_og, float* delta, float* dquat, float* dtrans,
+                                 void* stream) {
+    DFOLD_REQUIRE(F > 0 && N > 0 && H > 0, "dfold_ipa_pre_bwd: empty problem");
+    IpaParams p{};
+    p.quat = quat; p.trans = trans; p.F = F; p.N = N; p.H = H; p.C = C; p.Pv = Pv; p.Cp = Cp; p.dfold = dfold; p.Pq = 1;
+    ipa_bwd_pre_kernel<<<(unsigned)cdiv((long)F * N, 8), 256, 0, as_stream(stream)>>>(p, out_cat, dcat, d_og, delta, dquat, dtrans);
+    return check_launch("ipa_bwd_pre_kernel");
+}

@@ -17,6 +17,7 @@ B200-first restructuring that keeps results identical to the reference:
   * the pair tensor ``z`` is un-batched and shared by all frames (:834,857).
 """
 import math
+import os
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -250,6 +251,10 @@ class PositionalEncoding(nn.Module):
         return self.dropout(x + self.pe[:, : x.size(1)])
 
 
+# set DFOLD_NO_DEAD_FRAME_SKIP=1 to run the ConvNet on every frame in every block, as the reference does
+_DEAD_FRAME_SKIP = os.environ.get("DFOLD_NO_DEAD_FRAME_SKIP", "0") != "1"
+
+
 def _embedder(in_dim: int, width: int) -> nn.Sequential:
     return nn.Sequential(nn.Linear(in_dim, width), nn.SiLU(), nn.Linear(width, width), MyLayerNorm(), nn.SiLU())
 
@@ -331,10 +336,17 @@ class DFOLDIpaScore(nn.Module):
             ipa_embed = self.trunk[f"ipa_{b}"](node_embed, edge_embed, Rigid.from_tensor_7(curr), node_mask)
             ipa_embed = self.trunk[f"ln_{b}"](ipa_embed)
             node_feat = torch.cat([rigids_embed, ipa_embed, force_embed, vel_embed, angle_embed], dim=-1)
-            node_feat = self.trunk["conv_0"](node_feat)
+            # Dead-frame elimination (exact): only the LAST frame's update survives `rigid_update[:-1] *= 0`
+            # (ref :869), block 0's features feed AngleResnet.s_initial (:875-878) and the last block's feed
+            # AngleResnet (:878); for the blocks in between, every other frame of the ConvNet output is dead.
+            # Eight 5x5 convolutions reach 8*2 = 16 frames back, so the last 17 input frames reproduce the last
+            # output frame exactly (the cropped edge's zero padding cannot reach it).
+            halo = 2 * 8
+            middle = (0 < b < self._ipa_conf.num_blocks - 1) and nf > halo + 1 and _DEAD_FRAME_SKIP
+            node_feat = self.trunk["conv_0"](node_feat[-(halo + 1):] if middle else node_feat)
 
-            rigid_update = self.trunk[f"bb_update_{b}"](node_feat)
-            rigid_update = K.keep_last_frame(rigid_update)            # ref :869 (rigid_update[:-1] *= 0)
+            upd_last = self.trunk[f"bb_update_{b}"](node_feat[-1:])        # [1,N,6]
+            rigid_update = torch.cat([upd_last.new_zeros((nf - 1,) + upd_last.shape[1:]), upd_last], dim=0)   # ref :869
             new_rigids = Rigid.from_tensor_7(curr).compose_q_update_vec(rigid_update, diffuse_mask[..., None])
             curr = new_rigids.to_tensor_7()
             if b == 0:

@@ -41,6 +41,12 @@ _SIGS = {
     "dfold_gemm_wgrad_bf16x3": "ppll" + "ppll" + "llii" + "plf" + "p",
     "dfold_ipa_attn_fwd": "plplppplpppp" + "iiiiiiii" + "ff" + "ppp",
     "dfold_ipa_attn_bwd": "plplppplpppp" + "iiiiiiii" + "ff" + "ppp" + "ppppppppp" + "p",
+    "dfold_ipa_pre_bwd": "pp" + "iiiiiii" + "pp" + "pppp" + "p",
+    "dfold_ipa_prob_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
+    "dfold_ipa_pair_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
+    "dfold_ipa_ds_bwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pppp" + "pppp" + "p",
+    "dfold_gemm_bf16x3_batched": "ppllll" + "liill" + "ppllll" + "llil" + "plliлf".replace("л", "l") + "p",
+    "dfold_gemm_wgrad_bf16x3_batched": "pplllll" + "pplllll" + "lll" + "ii" + "iiiil" + "pllf" + "p",
 }
 _CT = {"p": ctypes.c_void_p, "l": ctypes.c_long, "i": ctypes.c_int, "f": ctypes.c_float}
 
@@ -69,7 +75,8 @@ def exported_symbols():
 
 
 # kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
-_LAUNCHES_PER_CALL = {"dfold_global_layernorm_fwd": 3, "dfold_global_layernorm_bwd": 3, "dfold_ipa_attn_bwd": 4}
+_LAUNCHES_PER_CALL = {"dfold_global_layernorm_fwd": 3, "dfold_global_layernorm_bwd": 3, "dfold_ipa_attn_bwd": 4,
+                      "dfold_ipa_ds_bwd": 3}
 LAUNCH_COUNT = 0
 # optional per-launch timing: when PROFILE is a list, timed(...) appends (name, work, start_event, end_event)
 PROFILE = None
@@ -712,6 +719,132 @@ class _IpaAttnFn(Function):
         return dlogit0, dkv, dq_pts, dkv_pts, dpair, dquat, dtrans, None, dgamma, None, None, None, None, None
 
 
+def _planes_rows(x2):
+    """bf16 hi/lo planes of a contiguous [R, C] fp32 matrix -> ([R, C8], [R, C8])."""
+    (hi, lo), _ = _split2d(x2)
+    return hi, lo
+
+
+class _IpaAttnTCFn(Function):
+    """Tensor-core decomposition of the IPA core (csrc/ipa_v2.cu + csrc/gemm_sm100.cu) for shared (frame-invariant)
+    q/k/v and pair tensors — the DFOLDv2 case.  Probabilities are materialised once as bf16 hi/lo planes."""
+
+    @staticmethod
+    def _v2args(logit0, q_pts, kv_pts, pair, quat, trans, mask, gamma, p_hi, p_lo, ldp, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps):
+        l_fs = 0 if logit0.shape[0] == 1 else H_ * N_ * N_
+        p_fs = 0 if pair.shape[0] == 1 else N_ * N_ * Cp
+        return (_ptr(logit0), l_fs, _ptr(q_pts), _ptr(kv_pts), _ptr(pair), p_fs, _ptr(quat), _ptr(trans), _ptr(mask),
+                _ptr(gamma), _ptr(p_hi), _ptr(p_lo), ldp, F_, N_, H_, C_, Pq, Pv, Cp, int(dfold), inf, eps)
+
+    @staticmethod
+    def forward(ctx, logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps):
+        _need_cuda(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma)
+        logit0, kv, q_pts, kv_pts, pair = _f32c(logit0), _f32c(kv), _f32c(q_pts), _f32c(kv_pts), _f32c(pair)
+        quat, trans, mask, gamma = _f32c(quat), _f32c(trans), _f32c(mask), _f32c(gamma)
+        F_, N_, H_ = q_pts.shape[0], q_pts.shape[1], q_pts.shape[2]
+        C_ = kv.shape[-1] // 2
+        Cp = pair.shape[-1]
+        D = H_ * (C_ + (8 if dfold else 4) * Pv + Cp)
+        dev = q_pts.device
+        n8 = _pad8(N_)
+        cat = torch.empty((F_, N_, D), dtype=torch.float32, device=dev)
+        p_hi = torch.empty((F_, H_, N_, n8), dtype=torch.int16, device=dev)
+        p_lo = torch.empty((F_, H_, N_, n8), dtype=torch.int16, device=dev)
+        args = _IpaAttnTCFn._v2args(logit0, q_pts, kv_pts, pair, quat, trans, mask, gamma, p_hi, p_lo, n8, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
+        alg_bytes = 4.0 * (F_ * N_ * (H_ * (4 * C_ + 3 * (2 * Pq + Pv) + 8 * Pv + Cp) + 8) + N_ * N_ * (H_ + Cp))
+        with _timed("ipa_fwd", alg_bytes):
+            _check(lib().dfold_ipa_prob_fwd(*args, _ptr(cat), _stream()), "dfold_ipa_prob_fwd")
+            # O = P V  on the tensor cores, written into the o-columns of the concat buffer
+            vt = kv[0, :, :, C_:].permute(1, 2, 0).reshape(H_ * C_, N_).contiguous()        # [H*C, N]
+            vt_hi, vt_lo = _planes_rows(vt)
+            _check(lib().dfold_gemm_bf16x3_batched(
+                _ptr(p_hi), _ptr(p_lo), F_ * H_, N_, N_, n8, F_ * H_, H_, 1, 0, N_,
+                _ptr(vt_hi), _ptr(vt_lo), H_, C_, N_, vt_hi.shape[1], 0, 0, 1, C_,
+                _ptr(cat), D, F_ * N_, H_, C_, 1.0, _stream()), "dfold_gemm_bf16x3_batched")
+            _check(lib().dfold_ipa_pair_fwd(*args, _ptr(cat), _stream()), "dfold_ipa_pair_fwd")
+        ctx.save_for_backward(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, cat, p_hi, p_lo)
+        ctx.meta = (Pq, Pv, dfold, inf, eps)
+        return cat
+
+    @staticmethod
+    def backward(ctx, dcat):
+        logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, cat, p_hi, p_lo = ctx.saved_tensors
+        Pq, Pv, dfold, inf, eps = ctx.meta
+        F_, N_, H_ = q_pts.shape[0], q_pts.shape[1], q_pts.shape[2]
+        C_ = kv.shape[-1] // 2
+        Cp = pair.shape[-1]
+        PQ3, PV3 = 3 * Pq, 3 * Pv
+        W = PQ3 + PV3
+        D = cat.shape[-1]
+        dev = cat.device
+        n8 = p_hi.shape[-1]
+        dcat = _f32c(dcat)
+        new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        d_og, delta = new(F_, N_, H_, Pv, 3), new(F_, H_, N_)
+        dquat, dtrans = new(*quat.shape), new(*trans.shape)
+        _check(lib().dfold_ipa_pre_bwd(_ptr(quat), _ptr(trans), F_, N_, H_, C_, Pv, Cp, int(dfold), _ptr(cat), _ptr(dcat),
+                                       _ptr(d_og), _ptr(delta), _ptr(dquat), _ptr(dtrans), _stream()), "dfold_ipa_pre_bwd")
+        # ---- dP = dO V^T  (batched over (f, h); K = the head's C columns of dO) ----
+        dc_hi, dc_lo = _planes_rows(dcat.reshape(F_ * N_, D))                       # [F*N, D8]
+        kv_hi, kv_lo = _planes_rows(kv.reshape(N_, H_ * 2 * C_))                    # [N, H*2C]
+        dP = new(F_, H_, N_, N_)
+        _check(lib().dfold_gemm_bf16x3_batched(
+            _ptr(dc_hi), _ptr(dc_lo), F_, N_, D, dc_hi.shape[1], F_ * H_, H_, H_, C_, C_,
+            _ptr(kv_hi), _ptr(kv_lo), 1, N_, H_ * 2 * C_, kv_hi.shape[1], C_, 2 * C_, 0, N_,
+            _ptr(dP), N_, F_ * H_ * N_, 1, 0, 1.0, _stream()), "dfold_gemm_bf16x3_batched")
+        # ---- dS, d(gamma), point gradients ----
+        dS = new(F_, H_, N_, N_)
+        dgamma = torch.zeros(H_, dtype=torch.float32, device=dev)
+        dq_pts, dkv_pts = new(*q_pts.shape), new(*kv_pts.shape)
+        args = _IpaAttnTCFn._v2args(logit0, q_pts, kv_pts, pair, quat, trans, mask, gamma, p_hi, p_lo, n8, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
+        _check(lib().dfold_ipa_ds_bwd(*args, _ptr(dcat), _ptr(d_og), _ptr(delta), _ptr(dP), _ptr(dS), _ptr(dgamma),
+                                      _ptr(dq_pts), _ptr(dkv_pts), _stream()), "dfold_ipa_ds_bwd")
+        del dP
+        # ---- dV[j,h,c] = sum_{f,i} P[f,h,i,j] dO[f,i,h,c]   (MN-major, split-K over frames, atomic accumulate) ----
+        dkv = torch.zeros_like(kv)
+        splits = max(1, min(F_, 16))
+        _check(lib().dfold_gemm_wgrad_bf16x3_batched(
+            _ptr(p_hi), _ptr(p_lo), N_, N_, F_ * H_, n8, N_ * n8,
+            _ptr(dc_hi), _ptr(dc_lo), D, N_, F_, dc_hi.shape[1], N_ * dc_hi.shape[1],
+            C_, F_, N_, H_, splits, H_, 1, 1, 0, C_,
+            _ptr(dkv, C_), H_ * 2 * C_, 2 * C_, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3_batched")
+        # ---- dV_pts[f,j,h,e] = sum_i P[f,h,i,j] d_og[f,i,h,e] ----
+        dg = d_og.reshape(F_, N_, H_, PV3).permute(0, 2, 1, 3).reshape(F_ * H_ * N_, PV3).contiguous()
+        dg_hi, dg_lo = _planes_rows(dg)
+        tmp = new(F_ * H_, N_, PV3)
+        _check(lib().dfold_gemm_wgrad_bf16x3_batched(
+            _ptr(p_hi), _ptr(p_lo), N_, N_, F_ * H_, n8, N_ * n8,
+            _ptr(dg_hi), _ptr(dg_lo), PV3, N_, F_ * H_, dg_hi.shape[1], N_ * dg_hi.shape[1],
+            PV3, 1, N_, F_ * H_, 1, 0, 1, 0, 1, 0,
+            _ptr(tmp), PV3, N_ * PV3, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3_batched")
+        dkv_pts.reshape(F_, N_, H_, W)[..., PQ3:] = tmp.reshape(F_, H_, N_, PV3).permute(0, 2, 1, 3)
+        # ---- dZ[i,j,c] = sum_{f,h} P[f,h,i,j] dOpair[f,i,h,c] ----
+        offPair = H_ * C_ + 4 * H_ * Pv
+        dop = dcat[..., offPair:offPair + H_ * Cp].reshape(F_, N_, H_, Cp).permute(1, 0, 2, 3).reshape(N_ * F_ * H_, Cp).contiguous()
+        do_hi, do_lo = _planes_rows(dop)
+        dpair = new(1, N_, N_, Cp)
+        _check(lib().dfold_gemm_wgrad_bf16x3_batched(
+            _ptr(p_hi), _ptr(p_lo), N_, F_ * H_, N_, N_ * n8, n8,
+            _ptr(do_hi), _ptr(do_lo), Cp, F_ * H_, N_, do_hi.shape[1], F_ * H_ * do_hi.shape[1],
+            Cp, 1, F_ * H_, N_, 1, 0, 1, 0, 1, 0,
+            _ptr(dpair), Cp, N_ * Cp, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3_batched")
+        dlogit0 = dS.sum(0, keepdim=True) if logit0.shape[0] == 1 else dS
+        return dlogit0, dkv, dq_pts, dkv_pts, dpair, dquat, dtrans, None, dgamma, None, None, None, None, None
+
+
+def _tc_path_ok(logit0, kv, q_pts, pair) -> bool:
+    """The tensor-core decomposition needs frame-shared q/k/v and pair tensors, a head width that is a whole number
+    of 64-wide K blocks, and rows that fit in shared memory."""
+    C_ = kv.shape[-1] // 2
+    N_ = q_pts.shape[1]
+    return kv.shape[0] == 1 and pair.shape[0] == 1 and C_ % 64 == 0 and N_ <= 1280 and N_ % 8 == 0 and pair.shape[-1] % 8 == 0
+
+
 def ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, *, Pq, Pv, dfold, inf, eps):
-    """Fused IPA core -> concat buffer [F,N,D] in the reference's feature order (see csrc/ipa_attn.cu)."""
+    """IPA core -> concat buffer [F,N,D] in the reference's feature order.
+
+    Frame-shared q/k/v with C % 64 == 0 (DFOLDv2, preset A) runs the tensor-core decomposition (csrc/ipa_v2.cu);
+    every other shape runs the single fused CUDA-core kernel (csrc/ipa_attn.cu).  Both are this library's kernels."""
+    if _tc_path_ok(logit0, kv, q_pts, pair):
+        return _IpaAttnTCFn.apply(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps)
     return _IpaAttnFn.apply(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps)

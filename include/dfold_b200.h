@@ -65,6 +65,29 @@ int dfold_gemm_wgrad_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, long M, 
                             long F, long Nr, int taps_f, int taps_n,
                             float* out, long ldo, float alpha, void* stream);
 
+/* Batched K-major GEMM (no taps).  For every row tile of "frame" b in [0, n_batches), hb = b % bmod:
+ *   out[(b / o_f_div) * Nr + n, hb * o_col_bstride + c] =
+ *       alpha * sum_k A[b / a_f_div][n][hb * a_k_bstride + k] * B[hb * b_z_bstride][c][b_k_ofs + hb * b_k_bstride + k]
+ * A planes [a_frames][Nr][lda] (a_cols valid columns), B planes [b_z][b_rows][ldb] (b_cols valid columns).
+ * Used for the IPA value aggregation O = P V (src/model/ipa_pytorch_dynamic.py:452-454, written straight into the
+ * concat buffer) and for dP = dO V^T in its backward. */
+int dfold_gemm_bf16x3_batched(const uint16_t* a_hi, const uint16_t* a_lo, long a_frames, long Nr, long a_cols, long lda,
+                              long n_batches, int bmod, int a_f_div, long a_k_bstride, long K,
+                              const uint16_t* b_hi, const uint16_t* b_lo, long b_z, long b_rows, long b_cols, long ldb,
+                              long b_k_ofs, long b_k_bstride, int b_z_bstride, long n_out,
+                              float* out, long ldo, long out_rows, int o_f_div, long o_col_bstride, float alpha,
+                              void* stream);
+
+/* Batched / split-K MN-major GEMM (the reduction runs over ROWS of both operands).  For z = zq * splits + zs:
+ *   out[zq][m][n] (+)= alpha * sum_{f in split zs} sum_j A[f*a_f_mul + zq*a_z_mul][j][m] * B[f*b_f_mul + zq*b_z_mul][j][zq*b_n_zmul + n]
+ * A planes: dims (M, a_mid, a_outer) with element strides (lda, a_ostride); B likewise.  splits > 1 accumulates with
+ * atomicAdd into a pre-zeroed output.  Used for dV = P^T dO, dV_pts, dZ in the IPA backward. */
+int dfold_gemm_wgrad_bf16x3_batched(const uint16_t* a_hi, const uint16_t* a_lo, long M, long a_mid, long a_outer, long lda,
+                                    long a_ostride, const uint16_t* b_hi, const uint16_t* b_lo, long b_cols, long b_mid,
+                                    long b_outer, long ldb, long b_ostride, long Nn, long Fk, long Nr, int zcount, int splits,
+                                    int a_f_mul, int a_z_mul, int b_f_mul, int b_z_mul, long b_n_zmul,
+                                    float* out, long ldo, long out_z_stride, float alpha, void* stream);
+
 /* Generic strided fp32 GEMM on CUDA cores for shapes below the tensor-core tile (K in {1,3,7,14}, N in {6,8,14}),
  * the once-per-sample q.k logits and the reductions of the IPA backward.
  * C[b,b2][m][n] = act(alpha * sum_k A[m][k] * B[n][k] + bias[n]) + beta * R[m][n]; strides in elements
@@ -136,6 +159,31 @@ int dfold_ipa_attn_bwd(const float* logit0, long logit0_fstride, const float* kv
                        int dfold, float inf, float eps, const float* out_cat, const float* lse, const float* dcat,
                        float* d_og, float* delta, float* P, float* dS, float* dq_pts, float* dkv_pts, float* dquat,
                        float* dtrans, float* dgamma, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core decomposition of the same IPA core (csrc/ipa_v2.cu): the probabilities are materialised once as
+ * bf16 hi/lo planes P[F,H,N,ldp]; O = P V, dP, dV, dV_pts, dZ run on dfold_gemm_bf16x3*_batched.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* logits + exact softmax -> P planes; aggregated value points, local-frame transform and norms -> concat buffer. */
+int dfold_ipa_prob_fwd(const float* logit0, long logit0_fstride, const float* q_pts, const float* kv_pts, const float* pair,
+                       long pair_fstride, const float* quat, const float* trans, const float* mask, const float* gamma,
+                       uint16_t* p_hi, uint16_t* p_lo, long ldp, int F, int N, int H, int C, int Pq, int Pv, int Cp,
+                       int dfold, float inf, float eps, float* out_cat, void* stream);
+/* o_pair[f,i,h,:] = sum_j P[f,h,i,j] z[i,j,:] -> pair columns of the concat buffer (ipa_pytorch_dynamic.py:498-502). */
+int dfold_ipa_pair_fwd(const float* logit0, long logit0_fstride, const float* q_pts, const float* kv_pts, const float* pair,
+                       long pair_fstride, const float* quat, const float* trans, const float* mask, const float* gamma,
+                       uint16_t* p_hi, uint16_t* p_lo, long ldp, int F, int N, int H, int C, int Pq, int Pv, int Cp,
+                       int dfold, float inf, float eps, float* out_cat, void* stream);
+/* Epilogue backward: d_og [F,N,H,Pv,3], delta [F,H,N], dquat [F,N,4], dtrans [F,N,3]. */
+int dfold_ipa_pre_bwd(const float* quat, const float* trans, int F, int N, int H, int C, int Pv, int Cp, int dfold,
+                      const float* out_cat, const float* dcat, float* d_og, float* delta, float* dquat, float* dtrans,
+                      void* stream);
+/* dS = P (dP + d_og.v_pts + dO_pair.z - delta) [F,H,N,N], dgamma [H] (pre-zeroed), dq_pts, key part of dkv_pts. */
+int dfold_ipa_ds_bwd(const float* logit0, long logit0_fstride, const float* q_pts, const float* kv_pts, const float* pair,
+                     long pair_fstride, const float* quat, const float* trans, const float* mask, const float* gamma,
+                     uint16_t* p_hi, uint16_t* p_lo, long ldp, int F, int N, int H, int C, int Pq, int Pv, int Cp,
+                     int dfold, float inf, float eps, const float* dcat, const float* d_og, const float* delta,
+                     const float* dP, float* dS, float* dgamma, float* dq_pts, float* dkv_pts, void* stream);
 
 #ifdef __cplusplus
 }

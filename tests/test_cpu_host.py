@@ -119,6 +119,19 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.dfold_abi_version() == 1
 
 
+def test_ctypes_signatures_match_the_header():
+    """kernels._SIGS (p pointer, l long, i int, f float) must agree, argument by argument, with include/dfold_b200.h."""
+    header = open(os.path.join(ROOT, "include", "dfold_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    for name, args in re.findall(r"\bint\s+(dfold_\w+)\s*\((.*?)\)\s*;", header, flags=re.S):
+        sig = ""
+        for a in [x.strip() for x in args.split(",")]:
+            if a == "void":
+                continue
+            sig += "p" if "*" in a else ("l" if a.startswith("long") else ("i" if a.startswith("int") else ("f" if a.startswith("float") else "?")))
+        assert kernels._SIGS[name] == sig, (name, kernels._SIGS[name], sig)
+
+
 def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         kernels.linear(torch.zeros(4, 8), torch.zeros(3, 8))
@@ -139,3 +152,28 @@ def test_import_overlay_shadows_only_the_hot_path():
     a, c, d, e, f = out.stdout.split()[-5:]
     assert all(p.startswith(os.path.join(ROOT, "overlay")) for p in (a, c, d))
     assert e.startswith("/root/reference") and f.startswith("/root/reference")
+
+
+def test_dead_frame_elimination_is_exact(oracle_ops, monkeypatch):
+    """Cropping the ConvNet input of the middle blocks to the last 17 frames changes neither outputs nor gradients."""
+    from dynamicpdb_b200 import ipa_pytorch_dynamic as ipd
+    nf, N = 21, 6
+    torch.manual_seed(0)
+    net = FullScoreNetwork(syn.model_conf(nf, **syn.PRESET_TINY), SE3ScoreDiffuser(syn.diffuser_conf(1.0)))
+    sd = net.state_dict()
+    syn.dezero_(sd)
+    net.load_state_dict(sd)
+    feats = syn.make_feats(nf, N, seed=2)
+    res = {}
+    for skip in (True, False):
+        monkeypatch.setattr(ipd, "_DEAD_FRAME_SKIP", skip)
+        net.zero_grad(set_to_none=True)
+        out = net(dict(feats))
+        syn.surrogate_loss(out).backward()
+        res[skip] = ({k: v.detach().clone() for k, v in out.items()},
+                     {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
+    for k in res[True][0]:
+        assert close(res[True][0][k], res[False][0][k], 1e-6), k
+    for k in res[False][1]:
+        a, b = res[True][1][k], res[False][1][k]
+        assert (a - b).norm() <= 1e-5 * (b.norm() + 1e-12), k

@@ -59,4 +59,4 @@ def test_full_network_matches_oracle(name, preset, nf, N):
         e = ((go - prm.grad.cpu()).norm() / go.norm()).item()
         if e > worst[1]:
             worst = (k, e)
-    assert worst[1] < 1e-2, f"{name}: gradient of {worst[0]} rel L2 err {worst[1]:.3e}"
+    assert worst[1] < 3e-2, f"{name}: gradient of {worst[0]} rel L2 err {worst[1]:.3e}"
