@@ -143,6 +143,7 @@ struct SgemmParams {
     const float* R; long r_rs, r_cs, r_bs, r_bs2;
     const float* bias;
     int nb2;
+    int ksplit;          // > 1: blockIdx.z also enumerates K chunks; partial sums are atomically added to a zeroed C
     int M, N, K;
     float alpha, beta;
     int act, pre_relu;
@@ -151,21 +152,24 @@ struct SgemmParams {
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
     __shared__ float As[16][65];
     __shared__ float Bs[16][65];
-    const int b = blockIdx.z / p.nb2, b2 = blockIdx.z % p.nb2;
+    const int zb = blockIdx.z / p.ksplit, ks = blockIdx.z % p.ksplit;
+    const int b = zb / p.nb2, b2 = zb % p.nb2;
+    const int kchunk = ((p.K + p.ksplit - 1) / p.ksplit + 15) / 16 * 16;
+    const int kbeg = ks * kchunk, kend = min(p.K, kbeg + kchunk);
     const float* A = p.A + (long)b * p.a_bs + (long)b2 * p.a_bs2;
     const float* B = p.B + (long)b * p.b_bs + (long)b2 * p.b_bs2;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;           // 16 x 16 threads, 4x4 outputs each
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < p.K; k0 += 16) {
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
 #pragma unroll
         for (int e = tid; e < 64 * 16; e += 256) {
             // choose the faster-varying index to follow the contiguous direction of the operand
             int mm, kk;
             if (p.a_cs == 1) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
             float v = 0.f;
-            if (m0 + mm < p.M && k0 + kk < p.K) {
+            if (m0 + mm < p.M && k0 + kk < kend) {
                 v = A[(long)(m0 + mm) * p.a_rs + (long)(k0 + kk) * p.a_cs];
                 if (p.pre_relu) v = fmaxf(v, 0.f);
             }
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
             int nn, kb;
             if (p.b_cs == 1) { kb = e & 15; nn = e >> 4; } else { nn = e & 63; kb = e >> 6; }
             float u = 0.f;
-            if (n0 + nn < p.N && k0 + kb < p.K) u = B[(long)(n0 + nn) * p.b_rs + (long)(k0 + kb) * p.b_cs];
+            if (n0 + nn < p.N && k0 + kb < kend) u = B[(long)(n0 + nn) * p.b_rs + (long)(k0 + kb) * p.b_cs];
             Bs[kb][nn] = u;
         }
         __syncthreads();
@@ -202,6 +206,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
             const int n = n0 + tx * 4 + j;
             if (n >= p.N) continue;
             float x = acc[i][j] * p.alpha;
+            if (p.ksplit > 1) {
+                atomicAdd(&C[(long)m * p.c_rs + (long)n * p.c_cs], x);
+                continue;
+            }
             if (p.bias) x += p.bias[n];
             if (p.act == 1) x = fmaxf(x, 0.f);
             else if (p.act == 2) x = x / (1.f + expf(-x));
@@ -393,17 +401,20 @@ extern "C" int dfold_taps_to_param(const float* g, int O, int I, int T, float* o
 }
 
 // Strides are in elements: *_rs row, *_cs column, *_bs / *_bs2 outer / inner batch.  C = act(alpha*A.B^T + bias) + beta*R.
+// ksplit > 1 splits the K range over extra CTAs (tiny-output weight gradients with K = all pixels) and atomically
+// accumulates into a zeroed C.
 extern "C" int dfold_sgemm(const float* A, long a_rs, long a_cs, long a_bs, long a_bs2,
                            const float* B, long b_rs, long b_cs, long b_bs, long b_bs2,
                            float* C, long c_rs, long c_cs, long c_bs, long c_bs2,
                            const float* R, long r_rs, long r_cs, long r_bs, long r_bs2,
                            const float* bias, int batch, int batch2, int M, int N, int K, float alpha, float beta, int act,
-                           int pre_relu, void* stream) {
-    DFOLD_REQUIRE(batch > 0 && batch2 > 0 && M > 0 && N > 0 && K >= 0, "dfold_sgemm: empty problem");
-    DFOLD_REQUIRE((long)batch * batch2 <= 65535, "dfold_sgemm: batch too large (%d x %d)", batch, batch2);
+                           int pre_relu, int ksplit, void* stream) {
+    DFOLD_REQUIRE(batch > 0 && batch2 > 0 && M > 0 && N > 0 && K >= 0 && ksplit >= 1, "dfold_sgemm: empty problem");
+    DFOLD_REQUIRE((long)batch * batch2 * ksplit <= 65535, "dfold_sgemm: batch too large (%d x %d x %d)", batch, batch2, ksplit);
+    DFOLD_REQUIRE(ksplit == 1 || (bias == nullptr && R == nullptr && act == 0), "dfold_sgemm: split-K takes no epilogue (C must be zeroed)");
     SgemmParams p{A, a_rs, a_cs, a_bs, a_bs2, B, b_rs, b_cs, b_bs, b_bs2, C, c_rs, c_cs, c_bs, c_bs2,
-                  R, r_rs, r_cs, r_bs, r_bs2, bias, batch2, M, N, K, alpha, beta, act, pre_relu};
-    dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64), (unsigned)(batch * batch2));
+                  R, r_rs, r_cs, r_bs, r_bs2, bias, batch2, ksplit, M, N, K, alpha, beta, act, pre_relu};
+    dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64), (unsigned)(batch * batch2 * ksplit));
     sgemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(p);
     return check_launch("sgemm_kernel");
 }

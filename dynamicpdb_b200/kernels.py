@@ -26,7 +26,7 @@ _SIGS = {
     "dfold_split2d": "plllipl" + "ppll" + "ppll" + "pp",
     "dfold_conv_weight_prep": "piii" + "ppl" + "ppl" + "p",
     "dfold_taps_to_param": "piiipp",
-    "dfold_sgemm": "pllll" * 4 + "p" + "iiiii" + "ff" + "ii" + "p",
+    "dfold_sgemm": "pllll" * 4 + "p" + "iiiii" + "ff" + "iii" + "p",
     "dfold_global_layernorm_fwd": "pppplfip",
     "dfold_global_layernorm_bwd": "pppppl" + "ip",
     "dfold_row_layernorm_fwd": "ppppplifp",
@@ -140,10 +140,10 @@ def _pad8(n: int) -> int:
 # --------------------------------------------------------------------------------------------------
 def _sgemm(A, a_off, a_rs, a_cs, a_bs, a_bs2, B, b_off, b_rs, b_cs, b_bs, b_bs2, C, c_off, c_rs, c_cs, c_bs, c_bs2,
            M, N, K, *, R=None, r_off=0, r_rs=0, r_cs=0, r_bs=0, r_bs2=0, bias=None, batch=1, batch2=1,
-           alpha=1.0, beta=1.0, act=0, pre_relu=0):
+           alpha=1.0, beta=1.0, act=0, pre_relu=0, ksplit=1):
     _check(lib().dfold_sgemm(_ptr(A, a_off), a_rs, a_cs, a_bs, a_bs2, _ptr(B, b_off), b_rs, b_cs, b_bs, b_bs2,
                              _ptr(C, c_off), c_rs, c_cs, c_bs, c_bs2, _ptr(R, r_off), r_rs, r_cs, r_bs, r_bs2,
-                             _ptr(bias), batch, batch2, M, N, K, alpha, beta, act, pre_relu, _stream()), "dfold_sgemm")
+                             _ptr(bias), batch, batch2, M, N, K, alpha, beta, act, pre_relu, ksplit, _stream()), "dfold_sgemm")
 
 
 def _split2d(x2: torch.Tensor, *, pre_relu=False, gate=None, want=True, want_t=False, colsum=None,
@@ -303,9 +303,12 @@ class _LinearFn(Function):
                 dx = torch.empty((M_, K_), dtype=torch.float32, device=g.device)
                 _sgemm(g, 0, N_, 1, 0, 0, wf, 0, 1, K_, 0, 0, dx, 0, K_, 1, 0, 0, M_, K_, N_)
             if need_w:
-                dw = torch.empty((N_, K_), dtype=torch.float32, device=g.device)
                 xr = torch.relu(x2) if pre_relu else x2
-                _sgemm(g, 0, 1, N_, 0, 0, xr, 0, 1, K_, 0, 0, dw, 0, K_, 1, 0, 0, N_, K_, M_)
+                # tiny [N, K] output reduced over all M rows: split the reduction over CTAs
+                tiles = ((N_ + 63) // 64) * ((K_ + 63) // 64)
+                ks = max(1, min(M_ // 512, 592 // tiles, 256))
+                dw = (torch.zeros if ks > 1 else torch.empty)((N_, K_), dtype=torch.float32, device=g.device)
+                _sgemm(g, 0, 1, N_, 0, 0, xr, 0, 1, K_, 0, 0, dw, 0, K_, 1, 0, 0, N_, K_, M_, ksplit=ks)
             if need_b:
                 db = g.sum(0)
         if dx is not None:

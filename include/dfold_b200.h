@@ -91,13 +91,14 @@ int dfold_gemm_wgrad_bf16x3_batched(const uint16_t* a_hi, const uint16_t* a_lo, 
 /* Generic strided fp32 GEMM on CUDA cores for shapes below the tensor-core tile (K in {1,3,7,14}, N in {6,8,14}),
  * the once-per-sample q.k logits and the reductions of the IPA backward.
  * C[b,b2][m][n] = act(alpha * sum_k A[m][k] * B[n][k] + bias[n]) + beta * R[m][n]; strides in elements
- * (*_rs row, *_cs column, *_bs outer batch, *_bs2 inner batch). */
+ * (*_rs row, *_cs column, *_bs outer batch, *_bs2 inner batch).  ksplit > 1: split-K with atomic accumulation into
+ * a pre-zeroed C (no bias / residual / activation). */
 int dfold_sgemm(const float* A, long a_rs, long a_cs, long a_bs, long a_bs2,
                 const float* B, long b_rs, long b_cs, long b_bs, long b_bs2,
                 float* C, long c_rs, long c_cs, long c_bs, long c_bs2,
                 const float* R, long r_rs, long r_cs, long r_bs, long r_bs2,
                 const float* bias, int batch, int batch2, int M, int N, int K, float alpha, float beta, int act,
-                int pre_relu, void* stream);
+                int pre_relu, int ksplit, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Norms

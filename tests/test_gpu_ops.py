@@ -89,7 +89,7 @@ def test_library_loads():
     assert K.lib().dfold_abi_version() == 1
 
 
-@pytest.mark.parametrize("M,Kd,N", [(5, 3, 16), (70, 14, 32), (33, 7, 6), (256, 160, 6), (100, 128, 8)])
+@pytest.mark.parametrize("M,Kd,N", [(5, 3, 16), (70, 14, 32), (33, 7, 6), (256, 160, 6), (100, 128, 8), (4096, 7, 6), (3000, 14, 32)])
 @pytest.mark.parametrize("act,pre_relu,res", [(None, False, False), ("relu", False, False), (None, True, True), ("silu", False, False)])
 def test_linear_simt(M, Kd, N, act, pre_relu, res):
     inputs = [R(M, Kd), R(N, Kd, scale=0.3), R(N)]
