@@ -5,8 +5,8 @@
     python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
     python bench.py --impl reference --steps K --warmup W    # the CPU oracle port, timed on the host cores
 
-A step = zero_grad + forward + surrogate loss + backward (+ NCCL gradient all-reduce through DDP when N > 1)
-+ Adam(amsgrad) step on ONE protein window of `--frames` frames x `--res` residues per rank (the only shape the
+A step = zero_grad + forward + surrogate loss + backward (+ one flat NCCL gradient all-reduce when N > 1)
++ Adam(amsgrad) step, captured in one CUDA graph (dynamicpdb_b200/train_step.py), on ONE protein window of `--frames` frames x `--res` residues per rank (the only shape the
 reference executes in one forward).  Weak scaling: every rank processes its own window.
 Prints ONE JSON line on rank 0.
 """
@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames in the bounded CPU sample")
     return ap.parse_args()
 
@@ -148,6 +149,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # required for capturing NCCL in a CUDA graph
         dist.init_process_group("nccl", device_id=dev)
     K.lib()
 
@@ -159,25 +161,15 @@ def run_ours(args):
     syn.dezero_(sd)
     net.load_state_dict(sd)
     net = net.to(dev)
-    model = net
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True,
-                                                          gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4, amsgrad=True)    # train_DFOLD_dynamics.py:412
-
+    from dynamicpdb_b200.train_step import TrainStep
     host = syn.make_feats(nf, N, seed=rank)                             # one protein window per rank
     host = {k: v.pin_memory() for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     resident = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-
-    def step(feats):
-        opt.zero_grad(set_to_none=True)
-        out = model(dict(feats))
-        loss = syn.surrogate_loss(out)
-        loss.backward()
-        opt.step()
-        return loss
+    # forward + loss + backward + flat NCCL gradient all-reduce + Adam(amsgrad), captured in one CUDA graph
+    ts = TrainStep(net, syn.surrogate_loss, resident, lr=1e-4, world_size=world, graph=not args.no_graph,
+                   warmup=max(3, args.warmup))
 
     def barrier():
         if world > 1:
@@ -190,11 +182,11 @@ def run_ours(args):
         e0.record()
         for _ in range(n):
             if e2e:
-                feats = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-                loss = step(feats)
-                loss_host.copy_(loss.detach().float(), non_blocking=True)
+                ts.load(host)                                          # H2D of this step's inputs (pinned host memory)
+                loss = ts()
+                loss_host.copy_(loss, non_blocking=True)               # D2H of the step's result
             else:
-                step(resident)
+                ts()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) / n
@@ -205,17 +197,22 @@ def run_ours(args):
         return ms
 
     for _ in range(args.warmup):
-        step(resident)
+        ts()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    K.LAUNCH_COUNT = 0
-    K.PROFILE = [] if rank == 0 else None
     ms = timed(args.steps, e2e=False)
-    launches = K.LAUNCH_COUNT // max(1, args.steps)
-    prof, K.PROFILE = K.PROFILE, None
     ms_e2e = timed(args.steps, e2e=True)
     clocks = sampler.stop() if sampler else None
+    # per-kernel durations: the same step, launched eagerly with CUDA events around the C-ABI launches
+    K.LAUNCH_COUNT = 0
+    K.PROFILE = [] if rank == 0 else None
+    prof_steps = 2
+    for _ in range(prof_steps):
+        ts._eager()
+    torch.cuda.synchronize()
+    launches = K.LAUNCH_COUNT // prof_steps
+    prof, K.PROFILE = K.PROFILE, None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -244,7 +241,8 @@ def run_ours(args):
         roof = {"kernel": "gemm_bf16x3_kernel (implicit 5x5 conv / linear, 3 bf16 MMAs per fp32 product)",
                 "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                 "peak_source": tf_src, "traffic": None, "launches_timed": n, "avg_launch_ms": 1e3 * t / n,
-                "share_of_step": (t / args.steps) / (ms * 1e-3), "tensor_pipe_frac": 3 * ach / tf_peak,
+                "share_of_step": (t / prof_steps) / (ms * 1e-3), "tensor_pipe_frac": 3 * ach / tf_peak,
+                "timed_in": "eager instrumented steps right after the timed (graph-replayed) region",
                 "note": "achieved counts fp32-equivalent FLOPs; the split issues 3 bf16 MMAs per product, so frac <= 1/3"}
     roof_ipa = None
     if "ipa_fwd" in agg:
@@ -252,8 +250,8 @@ def run_ours(args):
         ach = w / t / 1e9
         roof_ipa = {"kernel": "ipa_fwd_kernel (fused IPA core)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src, "traffic": None,
-                    "launches_timed": n, "avg_launch_ms": 1e3 * t / n, "share_of_step": (t / args.steps) / (ms * 1e-3),
-                    "note": "algorithmic bytes per SURVEY.md 8(d) (per-frame q/k/v formulation)"}
+                    "launches_timed": n, "avg_launch_ms": 1e3 * t / n, "share_of_step": (t / prof_steps) / (ms * 1e-3),
+                    "note": "prob kernel + tcgen05 P.V + pair kernel; algorithmic bytes per SURVEY.md 8(d) (per-frame q/k/v formulation)"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -268,7 +266,9 @@ def run_ours(args):
         "dtype": "f32 (bf16x3 split on tcgen05, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": f"DFOLDv2 training step fwd+bwd+Adam, N_res={N}, batch={nf} frames per rank (configs[2])",
                    "frames_per_rank": nf, "n_res": N, "preset": "train_DFOLDv2.yaml (c_s 256, c_z 128, C 256, H 8, Pq 8, Pv 12, 4 blocks)",
-                   "parallelism": f"dp{world}", "l2": "working set (weights 738 MB + activations) exceeds the 126 MB L2"},
+                   "parallelism": f"dp{world}", "l2": "working set (weights 738 MB + activations) exceeds the 126 MB L2",
+                   "cuda_graph": ts.graph is not None, "cuda_graph_error": ts.graph_error,
+                   "dead_frame_elimination": os.environ.get("DFOLD_NO_DEAD_FRAME_SKIP", "0") != "1"},
         "e2e": {"value": world * nf / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_ipa": roof_ipa, "cpu_baseline": cpu,

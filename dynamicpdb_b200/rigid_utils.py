@@ -136,8 +136,8 @@ def invert_rot_mat(rot_mat: torch.Tensor) -> torch.Tensor:
 
 def invert_quat(quat: torch.Tensor) -> torch.Tensor:
     """Conjugate / |q|^2. ref :282-286."""
-    sign = quat.new_tensor([1.0, -1.0, -1.0, -1.0])
-    return quat * sign / torch.sum(quat * quat, dim=-1, keepdim=True)
+    conj = torch.cat([quat[..., :1], -quat[..., 1:]], dim=-1)      # no host-side constant: stays graph-capturable
+    return conj / torch.sum(quat * quat, dim=-1, keepdim=True)
 
 
 # --------------------------------------------------------------------------------------------------
