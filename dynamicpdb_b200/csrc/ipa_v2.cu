@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) ipa_prob_fwd_kernel(const V2Params p) {
     float* s_q = s_rows + TI * LD;              // [TI][PQ3]
     float* s_k = s_q + TI * PQ3;                // [TJ][PQ3+1]
     float* s_opt = s_k + TJ * (PQ3 + 1);        // [TI][PV3]
+    float* s_v = s_opt + TI * PV3;              // [64][PV3]  value-point tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = blockIdx.x * TI, h = blockIdx.y, f = blockIdx.z;
 
@@ -118,19 +119,28 @@ __global__ void __launch_bounds__(256) ipa_prob_fwd_kernel(const V2Params p) {
         }
     }
     __syncthreads();
-    // ---- phase 3: aggregated global value points  o_pt[r][e] = sum_j P[r][j] v_pts[j][e] ----
+    // ---- phase 3: aggregated global value points  o_pt[r][e] = sum_j P[r][j] v_pts[j][e]  (key tiles of 64 in smem) ----
     {
         const int r = tid >> 3, g = tid & 7;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // comps g, g+8, ... (PV3 <= 64)
         const float* row = s_rows + r * LD;
         const float* vp = kvp + PQ3;
-        for (int j = 0; j < N; ++j) {
-            const float pv = row[j];
-            const float* v = vp + (long)j * H * W;
+        for (int j0 = 0; j0 < N; j0 += 64) {
+            __syncthreads();
+            for (int e = tid; e < 64 * PV3; e += 256) {
+                const int jj = e / PV3, c = e % PV3, j = j0 + jj;
+                s_v[e] = (j < N) ? vp[(long)j * H * W + c] : 0.f;
+            }
+            __syncthreads();
+            const int jn = min(64, N - j0);
+            for (int jj = 0; jj < jn; ++jj) {
+                const float pv = row[j0 + jj];
+                const float* v = s_v + jj * PV3;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int e = g + 8 * m;
-                if (e < PV3) acc[m] = fmaf(pv, __ldg(v + e), acc[m]);
+                for (int m = 0; m < 8; ++m) {
+                    const int e = g + 8 * m;
+                    if (e < PV3) acc[m] = fmaf(pv, v[e], acc[m]);
+                }
             }
         }
 #pragma unroll
@@ -167,36 +177,62 @@ __global__ void __launch_bounds__(256) ipa_prob_fwd_kernel(const V2Params p) {
     }
 }
 
-// o_pair[f,i,h,c] = sum_j P[f,h,i,j] z[i,j,c].  grid (N, F), 256 threads (8 warps); smem p[H][N]
-__global__ void __launch_bounds__(256) ipa_pair_fwd_kernel(const V2Params p) {
+// o_pair[f,i,h,c] = sum_j P[f,h,i,j] z[i,j,c].  grid (N, ceil(F/FG)), 256 threads (8 warps).
+// smem: p[H][N] and, when it fits (stage_z), the residue's whole pair row z[i][:][:] — read once and reused by the FG
+// frames and all heads of the CTA.
+constexpr int FG = 8;
+__global__ void __launch_bounds__(256) ipa_pair_fwd_kernel(const V2Params p, int stage_z) {
     extern __shared__ float sm[];
     const int N = p.N, H = p.H, Cp = p.Cp;
-    const int i = blockIdx.x, f = blockIdx.y;
+    const int i = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < H * N; e += 256) {
-        const int h = e / N, j = e % N;
-        const long o = (((long)f * H + h) * N + i) * p.ldp + j;
-        sm[e] = join_bf16(p.p_hi[o], p.p_lo[o]);
-    }
-    __syncthreads();
-    const float* z = p.pair + (long)f * p.pair_fs + (long)i * N * Cp;
+    float* s_p = sm;                          // [H][N]
+    float* s_z = sm + H * N;                  // [N][Cp]  (stage_z)
     const int D = cat_width(p);
     const int offPair = H * p.C + 4 * H * p.Pv;
-    float* orow = p.cat + ((long)f * N + i) * D + offPair;
-    for (int h = warp; h < H; h += 8) {
-        const float* ph = sm + h * N;
-        for (int c0 = 0; c0 < Cp; c0 += 32) {
-            const int c = c0 + lane;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            if (c < Cp) {
+    const bool shared_z = (p.pair_fs == 0);
+    if (stage_z && shared_z) {
+        const float4* src = reinterpret_cast<const float4*>(p.pair + (long)i * N * Cp);
+        float4* dst = reinterpret_cast<float4*>(s_z);
+        for (int e = tid; e < N * Cp / 4; e += 256) dst[e] = __ldg(src + e);
+    }
+    for (int f = blockIdx.y * FG; f < min(p.F, (int)(blockIdx.y + 1) * FG); ++f) {
+        __syncthreads();
+        for (int e = tid; e < H * N; e += 256) {
+            const int h = e / N, j = e % N;
+            const long o = (((long)f * H + h) * N + i) * p.ldp + j;
+            s_p[e] = join_bf16(p.p_hi[o], p.p_lo[o]);
+        }
+        if (stage_z && !shared_z) {
+            const float4* src = reinterpret_cast<const float4*>(p.pair + (long)f * p.pair_fs + (long)i * N * Cp);
+            float4* dst = reinterpret_cast<float4*>(s_z);
+            for (int e = tid; e < N * Cp / 4; e += 256) dst[e] = __ldg(src + e);
+        }
+        __syncthreads();
+        const float* zg = p.pair + (long)f * p.pair_fs + (long)i * N * Cp;
+        float* orow = p.cat + ((long)f * N + i) * D + offPair;
+        for (int h = warp; h < H; h += 8) {
+            const float* ph = s_p + h * N;
+            for (int c0 = 0; c0 < Cp; c0 += 32) {
+                const int c = c0 + lane;
+                if (c >= Cp) continue;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                 int j = 0;
-                for (; j + 4 <= N; j += 4) {
-                    const float z0 = __ldg(z + (long)j * Cp + c), z1 = __ldg(z + (long)(j + 1) * Cp + c);
-                    const float z2 = __ldg(z + (long)(j + 2) * Cp + c), z3 = __ldg(z + (long)(j + 3) * Cp + c);
-                    a0 = fmaf(ph[j], z0, a0); a1 = fmaf(ph[j + 1], z1, a1);
-                    a2 = fmaf(ph[j + 2], z2, a2); a3 = fmaf(ph[j + 3], z3, a3);
+                if (stage_z) {
+                    for (; j + 4 <= N; j += 4) {
+                        a0 = fmaf(ph[j], s_z[j * Cp + c], a0); a1 = fmaf(ph[j + 1], s_z[(j + 1) * Cp + c], a1);
+                        a2 = fmaf(ph[j + 2], s_z[(j + 2) * Cp + c], a2); a3 = fmaf(ph[j + 3], s_z[(j + 3) * Cp + c], a3);
+                    }
+                    for (; j < N; ++j) a0 = fmaf(ph[j], s_z[j * Cp + c], a0);
+                } else {
+                    for (; j + 4 <= N; j += 4) {
+                        const float z0 = __ldg(zg + (long)j * Cp + c), z1 = __ldg(zg + (long)(j + 1) * Cp + c);
+                        const float z2 = __ldg(zg + (long)(j + 2) * Cp + c), z3 = __ldg(zg + (long)(j + 3) * Cp + c);
+                        a0 = fmaf(ph[j], z0, a0); a1 = fmaf(ph[j + 1], z1, a1);
+                        a2 = fmaf(ph[j + 2], z2, a2); a3 = fmaf(ph[j + 3], z3, a3);
+                    }
+                    for (; j < N; ++j) a0 = fmaf(ph[j], __ldg(zg + (long)j * Cp + c), a0);
                 }
-                for (; j < N; ++j) a0 = fmaf(ph[j], __ldg(z + (long)j * Cp + c), a0);
                 orow[h * Cp + c] = (a0 + a1) + (a2 + a3);
             }
         }
@@ -207,6 +243,7 @@ __global__ void __launch_bounds__(256) ipa_pair_fwd_kernel(const V2Params p) {
 // grid (ceil(N/32), H, F), 256 threads: 4 rows per warp, keys across lanes.
 __global__ void __launch_bounds__(256) ipa_ds_kernel(const V2Params p, const float* __restrict__ dcat, const float* __restrict__ d_og,
                                                      const float* __restrict__ delta, const float* __restrict__ dPg,
+                                                     const float* __restrict__ Tz,
                                                      float* __restrict__ dS, float* __restrict__ dgamma) {
     extern __shared__ float sm[];
     const int N = p.N, H = p.H, Cp = p.Cp;
@@ -262,12 +299,16 @@ __global__ void __launch_bounds__(256) ipa_ds_kernel(const V2Params p, const flo
             float dp = dPg[o];
             const float* dg = s_dog + r * PV3;
             for (int c = 0; c < PV3; ++c) dp = fmaf(dg[c], kp[PQ3 + c], dp);
-            const float* zr = zbase + ((long)i * N + j) * Cp;
-            const float* dz = s_dop + r * Cp;
-            for (int c = 0; c < Cp; c += 4) {
-                const float4 z = __ldg(reinterpret_cast<const float4*>(zr + c));
-                dp = fmaf(dz[c], z.x, dp); dp = fmaf(dz[c + 1], z.y, dp);
-                dp = fmaf(dz[c + 2], z.z, dp); dp = fmaf(dz[c + 3], z.w, dp);
+            if (Tz) {
+                dp += Tz[((long)i * p.F * H + (long)f * H + h) * N + j];      // sum_c dOpair[f,i,h,c] z[i,j,c]
+            } else {
+                const float* zr = zbase + ((long)i * N + j) * Cp;
+                const float* dz = s_dop + r * Cp;
+                for (int c = 0; c < Cp; c += 4) {
+                    const float4 z = __ldg(reinterpret_cast<const float4*>(zr + c));
+                    dp = fmaf(dz[c], z.x, dp); dp = fmaf(dz[c + 1], z.y, dp);
+                    dp = fmaf(dz[c + 2], z.z, dp); dp = fmaf(dz[c + 3], z.w, dp);
+                }
             }
             const float ds = pv * (dp - dl[rr]);
             dS[o] = ds;
@@ -389,7 +430,7 @@ extern "C" int dfold_ipa_prob_fwd(V2_ARGS, float* out_cat, void* stream) {
                   F, N, H, C, Pq, Pv, Cp, dfold, inf, eps)) return 1;
     p.cat = out_cat;
     const int PQ3 = Pq * 3, PV3 = Pv * 3;
-    const size_t smem = sizeof(float) * (size_t)(TI * (N + 1) + TI * PQ3 + TJ * (PQ3 + 1) + TI * PV3);
+    const size_t smem = sizeof(float) * (size_t)(TI * (N + 1) + TI * PQ3 + TJ * (PQ3 + 1) + TI * PV3 + 64 * PV3);
     if (set_smem(ipa_prob_fwd_kernel, smem, "ipa_prob_fwd")) return 1;
     dim3 grid((unsigned)cdiv(N, TI), (unsigned)H, (unsigned)F);
     ipa_prob_fwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(p);
@@ -401,16 +442,19 @@ extern "C" int dfold_ipa_pair_fwd(V2_ARGS, float* out_cat, void* stream) {
     if (v2_params(p, logit0, logit0_fstride, q_pts, kv_pts, pair, pair_fstride, quat, trans, mask, gamma, p_hi, p_lo, ldp,
                   F, N, H, C, Pq, Pv, Cp, dfold, inf, eps)) return 1;
     p.cat = out_cat;
-    const size_t smem = sizeof(float) * (size_t)H * N;
+    size_t smem = sizeof(float) * ((size_t)H * N + (size_t)N * Cp);
+    int stage_z = 1;
+    if (smem > 160 * 1024) { smem = sizeof(float) * (size_t)H * N; stage_z = 0; }
     if (set_smem(ipa_pair_fwd_kernel, smem, "ipa_pair_fwd")) return 1;
-    dim3 grid((unsigned)N, (unsigned)F);
-    ipa_pair_fwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(p);
+    dim3 grid((unsigned)N, (unsigned)cdiv(F, FG));
+    ipa_pair_fwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(p, stage_z);
     return check_launch("ipa_pair_fwd_kernel");
 }
 
 // dS [F,H,N,N] from the GEMM-produced dP [F,H,N,N]; dgamma [H] pre-zeroed.  Then the two point-gradient passes.
+// Tz (nullable): the pair term sum_c dOpair[f,i,h,c] z[i,j,c] precomputed as [N(i)][F*H][N(j)] on the tensor cores.
 extern "C" int dfold_ipa_ds_bwd(V2_ARGS, const float* dcat, const float* d_og, const float* delta, const float* dP,
-                                float* dS, float* dgamma, float* dq_pts, float* dkv_pts, void* stream) {
+                                const float* Tz, float* dS, float* dgamma, float* dq_pts, float* dkv_pts, void* stream) {
     V2Params p;
     if (v2_params(p, logit0, logit0_fstride, q_pts, kv_pts, pair, pair_fstride, quat, trans, mask, gamma, p_hi, p_lo, ldp,
                   F, N, H, C, Pq, Pv, Cp, dfold, inf, eps)) return 1;
@@ -419,7 +463,7 @@ extern "C" int dfold_ipa_ds_bwd(V2_ARGS, const float* dcat, const float* d_og, c
     const size_t smem = sizeof(float) * (size_t)(TI * PQ3 + TJ * (W + 1) + TI * PV3 + TI * Cp);
     if (set_smem(ipa_ds_kernel, smem, "ipa_ds")) return 1;
     dim3 grid((unsigned)cdiv(N, TI), (unsigned)H, (unsigned)F);
-    ipa_ds_kernel<<<grid, 256, smem, st>>>(p, dcat, d_og, delta, dP, dS, dgamma);
+    ipa_ds_kernel<<<grid, 256, smem, st>>>(p, dcat, d_og, delta, dP, Tz, dS, dgamma);
     if (check_launch("ipa_ds_kernel")) return 1;
     const size_t smem2 = sizeof(float) * (size_t)(32 * PQ3 + 32 * (PQ3 + 1));
     ipa_pts_grad_kernel<<<grid, 256, smem2, st>>>(p, dS, dq_pts, dkv_pts, 0);

@@ -88,26 +88,37 @@ __global__ void split2d_kernel(const float* __restrict__ x, long R, long C, long
 // conv weight w[O][I][T] (T = taps, contiguous) ->
 //   fwd planes   [T][O][ldi]   (K = I contiguous)
 //   dgrad planes [T][I][ldo_]  (K = O contiguous), tap index flipped (T-1-t)
-__global__ void conv_weight_prep_kernel(const float* __restrict__ w, int O, int I, int T,
+// One CTA per 32 x 32 (o, i) tile: the tile is read with 32 contiguous runs of 32*T floats and both plane sets are
+// written in 64-byte runs (i-contiguous for the forward planes, o-contiguous for the dgrad planes).
+__global__ void __launch_bounds__(256) conv_weight_prep_kernel(const float* __restrict__ w, int O, int I, int T,
                                         uint16_t* __restrict__ f_hi, uint16_t* __restrict__ f_lo, long ldi,
                                         uint16_t* __restrict__ d_hi, uint16_t* __restrict__ d_lo, long ldo_) {
-    // one CTA per (o, chunk of 64 input channels)
-    extern __shared__ uint32_t sm[];                  // [64][T]
-    const int o = blockIdx.y;
-    const int i0 = blockIdx.x * 64;
-    const int ni = min(64, I - i0);
-    const float* src = w + ((long)o * I + i0) * T;
-    for (int e = threadIdx.x; e < ni * T; e += blockDim.x) sm[e] = split_pack(src[e]);
+    extern __shared__ uint32_t sm[];                  // [32 o][32 i][T]  (+1 padding per o row)
+    const int o0 = blockIdx.y * 32, i0 = blockIdx.x * 32;
+    const int no = min(32, O - o0), ni = min(32, I - i0);
+    const int row = 32 * T + 1;
+    for (int oo = 0; oo < no; ++oo) {
+        const float* src = w + ((long)(o0 + oo) * I + i0) * T;
+        for (int e = threadIdx.x; e < ni * T; e += blockDim.x) sm[oo * row + e] = split_pack(src[e]);
+    }
     __syncthreads();
-    for (int e = threadIdx.x; e < T * 64; e += blockDim.x) {
-        const int t = e / 64, ii = e % 64;
-        if (ii < ni) {
-            const uint32_t pk = sm[ii * T + t];
-            const long fo = ((long)t * O + o) * ldi + i0 + ii;
+    // forward planes: (t, o) rows, i contiguous
+    for (int e = threadIdx.x; e < T * 32 * 32; e += blockDim.x) {
+        const int ii = e & 31, oo = (e >> 5) & 31, t = e >> 10;
+        if (ii < ni && oo < no) {
+            const uint32_t pk = sm[oo * row + ii * T + t];
+            const long fo = ((long)t * O + o0 + oo) * ldi + i0 + ii;
             f_hi[fo] = (uint16_t)(pk >> 16);
             f_lo[fo] = (uint16_t)(pk & 0xffffu);
-            if (d_hi) {
-                const long dofs = ((long)(T - 1 - t) * I + i0 + ii) * ldo_ + o;
+        }
+    }
+    if (d_hi) {
+        // dgrad planes: (t', i) rows, o contiguous
+        for (int e = threadIdx.x; e < T * 32 * 32; e += blockDim.x) {
+            const int oo = e & 31, ii = (e >> 5) & 31, t = e >> 10;
+            if (ii < ni && oo < no) {
+                const uint32_t pk = sm[oo * row + ii * T + t];
+                const long dofs = ((long)(T - 1 - t) * I + i0 + ii) * ldo_ + o0 + oo;
                 d_hi[dofs] = (uint16_t)(pk >> 16);
                 d_lo[dofs] = (uint16_t)(pk & 0xffffu);
             }
@@ -388,8 +399,15 @@ extern "C" int dfold_conv_weight_prep(const float* w, int O, int I, int T, uint1
                                       uint16_t* d_hi, uint16_t* d_lo, long ldo, void* stream) {
     DFOLD_REQUIRE(O > 0 && I > 0 && T > 0 && T <= 64, "dfold_conv_weight_prep: bad shape");
     DFOLD_REQUIRE(ldi >= I && (d_hi == nullptr || ldo >= O), "dfold_conv_weight_prep: bad leading dims");
-    dim3 grid((unsigned)cdiv(I, 64), (unsigned)O);
-    conv_weight_prep_kernel<<<grid, 256, 64 * T * sizeof(uint32_t), as_stream(stream)>>>(w, O, I, T, f_hi, f_lo, ldi, d_hi, d_lo, ldo);
+    dim3 grid((unsigned)cdiv(I, 32), (unsigned)cdiv(O, 32));
+    const size_t smem = (size_t)32 * (32 * T + 1) * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(conv_weight_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        DFOLD_REQUIRE(e == cudaSuccess, "conv_weight_prep: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    conv_weight_prep_kernel<<<grid, 256, smem, as_stream(stream)>>>(w, O, I, T, f_hi, f_lo, ldi, d_hi, d_lo, ldo);
     return check_launch("conv_weight_prep_kernel");
 }
 

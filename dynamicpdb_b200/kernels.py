@@ -44,7 +44,7 @@ _SIGS = {
     "dfold_ipa_pre_bwd": "pp" + "iiiiiii" + "pp" + "pppp" + "p",
     "dfold_ipa_prob_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
     "dfold_ipa_pair_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
-    "dfold_ipa_ds_bwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pppp" + "pppp" + "p",
+    "dfold_ipa_ds_bwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "ppppp" + "pppp" + "p",
     "dfold_gemm_bf16x3_batched": "ppllll" + "liill" + "ppllll" + "llil" + "plliлf".replace("л", "l") + "p",
     "dfold_gemm_wgrad_bf16x3_batched": "pplllll" + "pplllll" + "lll" + "ii" + "iiiil" + "pllf" + "p",
 }
@@ -795,13 +795,24 @@ class _IpaAttnTCFn(Function):
             _ptr(dc_hi), _ptr(dc_lo), F_, N_, D, dc_hi.shape[1], F_ * H_, H_, H_, C_, C_,
             _ptr(kv_hi), _ptr(kv_lo), 1, N_, H_ * 2 * C_, kv_hi.shape[1], C_, 2 * C_, 0, N_,
             _ptr(dP), N_, F_ * H_ * N_, 1, 0, 1.0, _stream()), "dfold_gemm_bf16x3_batched")
+        # ---- pair term of dP on the tensor cores:  Tz[i][f*H+h][j] = sum_c dOpair[f,i,h,c] z[i,j,c]  (batched over i) ----
+        offPair = H_ * C_ + 4 * H_ * Pv
+        dop = dcat[..., offPair:offPair + H_ * Cp].reshape(F_, N_, H_, Cp).permute(1, 0, 2, 3).reshape(N_ * F_ * H_, Cp).contiguous()
+        do_hi, do_lo = _planes_rows(dop)                                           # [N*F*H, Cp8]  rows (i, f, h)
+        z_hi, z_lo = _planes_rows(pair.reshape(N_ * N_, Cp))                       # [N*N, Cp8]    rows (i, j)
+        Tz = new(N_, F_ * H_, N_)
+        _check(lib().dfold_gemm_bf16x3_batched(
+            _ptr(do_hi), _ptr(do_lo), N_, F_ * H_, Cp, do_hi.shape[1], N_, N_, 1, 0, Cp,
+            _ptr(z_hi), _ptr(z_lo), N_, N_, Cp, z_hi.shape[1], 0, 0, 1, N_,
+            _ptr(Tz), N_, N_ * F_ * H_, 1, 0, 1.0, _stream()), "dfold_gemm_bf16x3_batched")
         # ---- dS, d(gamma), point gradients ----
         dS = new(F_, H_, N_, N_)
         dgamma = torch.zeros(H_, dtype=torch.float32, device=dev)
         dq_pts, dkv_pts = new(*q_pts.shape), new(*kv_pts.shape)
         args = _IpaAttnTCFn._v2args(logit0, q_pts, kv_pts, pair, quat, trans, mask, gamma, p_hi, p_lo, n8, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
-        _check(lib().dfold_ipa_ds_bwd(*args, _ptr(dcat), _ptr(d_og), _ptr(delta), _ptr(dP), _ptr(dS), _ptr(dgamma),
+        _check(lib().dfold_ipa_ds_bwd(*args, _ptr(dcat), _ptr(d_og), _ptr(delta), _ptr(dP), _ptr(Tz), _ptr(dS), _ptr(dgamma),
                                       _ptr(dq_pts), _ptr(dkv_pts), _stream()), "dfold_ipa_ds_bwd")
+        del Tz
         del dP
         # ---- dV[j,h,c] = sum_{f,i} P[f,h,i,j] dO[f,i,h,c]   (MN-major, split-K over frames, atomic accumulate) ----
         dkv = torch.zeros_like(kv)
@@ -822,9 +833,6 @@ class _IpaAttnTCFn(Function):
             _ptr(tmp), PV3, N_ * PV3, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3_batched")
         dkv_pts.reshape(F_, N_, H_, W)[..., PQ3:] = tmp.reshape(F_, H_, N_, PV3).permute(0, 2, 1, 3)
         # ---- dZ[i,j,c] = sum_{f,h} P[f,h,i,j] dOpair[f,i,h,c] ----
-        offPair = H_ * C_ + 4 * H_ * Pv
-        dop = dcat[..., offPair:offPair + H_ * Cp].reshape(F_, N_, H_, Cp).permute(1, 0, 2, 3).reshape(N_ * F_ * H_, Cp).contiguous()
-        do_hi, do_lo = _planes_rows(dop)
         dpair = new(1, N_, N_, Cp)
         _check(lib().dfold_gemm_wgrad_bf16x3_batched(
             _ptr(p_hi), _ptr(p_lo), N_, F_ * H_, N_, N_ * n8, n8,
