@@ -129,12 +129,17 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
 # the CUDA path
 # --------------------------------------------------------------------------------------------------
+def _log(msg):
+    if os.environ.get("DFOLD_BENCH_VERBOSE", "0") == "1":
+        print(f"[bench rank {os.environ.get('RANK', '0')} t={time.perf_counter():.1f}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch.distributed as dist
     from dynamicpdb_b200 import kernels as K
@@ -152,6 +157,7 @@ def run_ours(args):
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # required for capturing NCCL in a CUDA graph
         dist.init_process_group("nccl", device_id=dev)
     K.lib()
+    _log("process group + library ready")
 
     nf, N = args.frames, args.res
     torch.manual_seed(0)
@@ -161,6 +167,7 @@ def run_ours(args):
     syn.dezero_(sd)
     net.load_state_dict(sd)
     net = net.to(dev)
+    _log("model on device")
     from dynamicpdb_b200.train_step import TrainStep
     host = syn.make_feats(nf, N, seed=rank)                             # one protein window per rank
     host = {k: v.pin_memory() for k, v in host.items()}
@@ -170,6 +177,8 @@ def run_ours(args):
     # forward + loss + backward + flat NCCL gradient all-reduce + Adam(amsgrad), captured in one CUDA graph
     ts = TrainStep(net, syn.surrogate_loss, resident, lr=1e-4, world_size=world, graph=not args.no_graph,
                    warmup=max(3, args.warmup))
+
+    _log(f"train step ready (graph={ts.graph is not None}, err={ts.graph_error})")
 
     def barrier():
         if world > 1:
@@ -202,7 +211,9 @@ def run_ours(args):
     if sampler:
         sampler.start()
     ms = timed(args.steps, e2e=False)
+    _log(f"timed region done: {ms:.1f} ms/step")
     ms_e2e = timed(args.steps, e2e=True)
+    _log("e2e region done")
     clocks = sampler.stop() if sampler else None
     # per-kernel durations: the same step, launched eagerly with CUDA events around the C-ABI launches
     K.LAUNCH_COUNT = 0
@@ -214,8 +225,7 @@ def run_ours(args):
     launches = K.LAUNCH_COUNT // prof_steps
     prof, K.PROFILE = K.PROFILE, None
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dist)
         return
 
     # ---- roofline of the dominant kernel (the split-bf16 tensor-core GEMM) and of the fused IPA forward ----
@@ -273,9 +283,22 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_ipa": roof_ipa, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    _finish(world, dist)
+
+
+def _finish(world, dist):
+    """Leave without tearing the NCCL communicator down: destroy_process_group() blocks while a captured CUDA graph
+    still references the communicator.  Every rank has finished measuring (the timed regions end with barriers)."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+        except Exception:       # noqa: BLE001
+            pass
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -64,6 +64,8 @@ struct GemmParams {
     int b_k_ofs;         // B K-coordinate offset         = b_k_ofs + hb * b_k_bstride
     int b_k_bstride;
     int b_z_bstride;     // B third coordinate            = tap + hb * b_z_bstride
+    int f_start;         // A frame coordinate offset (output frame f reads input frames f + f_start + df): cropped convs
+    int b_f_add;         // mode 1: B outer coordinate offset
     int o_f_div;         // output row                    = (f0 / o_f_div) * Nr + n
     long o_col_bstride;  // output column offset          = hb * o_col_bstride
     // mode 1: blockIdx.z = zq * zdiv + zs  (zq: tap or batch id, zs: K split)
@@ -224,7 +226,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const int dn = tap % p.taps_n - p.taps_n / 2;
                     const int df = tap / p.taps_n - p.taps_f / 2;
                     const int ak = c * BK + hb * p.a_k_bstride;
-                    const int af = f0 / p.a_f_div + df;
+                    const int af = f0 / p.a_f_div + p.f_start + df;
                     const int bk = c * BK + p.b_k_ofs + hb * p.b_k_bstride;
                     const int bz = tap + hb * p.b_z_bstride;
                     tma_load_3d(sa_hi, &map_a_hi, full_bar(s), ak, n0 + dn, af);
@@ -241,7 +243,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     const int dn = has_taps ? zq % p.taps_n - p.taps_n / 2 : 0;
                     const int df = has_taps ? zq / p.taps_n - p.taps_f / 2 : 0;
                     const int af = f * p.a_f_mul + zq * p.a_z_mul;
-                    const int bf = f * p.b_f_mul + zq * p.b_z_mul + df;
+                    const int bf = f * p.b_f_mul + zq * p.b_z_mul + p.b_f_add + df;
                     const int bn0 = col0 + zq * p.b_n_zmul;
 #pragma unroll
                     for (int a = 0; a < BM / 64; ++a) {
@@ -430,15 +432,31 @@ int launch(const CUtensorMap* maps, const GemmParams& p, dim3 grid, cudaStream_t
 
 void default_batching(GemmParams& p) {
     p.bmod = 1; p.a_f_div = 1; p.a_k_bstride = 0; p.b_k_ofs = 0; p.b_k_bstride = 0; p.b_z_bstride = 0;
-    p.o_f_div = 1; p.o_col_bstride = 0;
+    p.o_f_div = 1; p.o_col_bstride = 0; p.f_start = 0; p.b_f_add = 0;
     p.zdiv = 1; p.a_f_mul = 1; p.a_z_mul = 0; p.b_f_mul = 1; p.b_z_mul = 0; p.b_n_zmul = 0;
     p.kb_per_split = p.num_kb; p.atomic = 0;
 }
 
-int pick_bn(long n_out) {
-    if (n_out % 256 == 0 || n_out > 640) return 256;
-    if (n_out > 64) return 128;
-    return 64;
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// Tile width: every CTA owns one SM (192 KB of shared memory), so the launch runs in ceil(tiles / SMs) waves whose
+// duration is proportional to BN.  Pick the width with the smallest waves x BN (ties -> the wider tile, which re-reads
+// the A operand less).  `row_tiles` = 128-row tiles x batches / taps in the other grid dimensions.
+int pick_bn(long n_out, long row_tiles) {
+    if (n_out <= 64) return 64;
+    if (n_out <= 128) return 128;
+    const long sms = sm_count();
+    const long t256 = cdiv(n_out, 256) * row_tiles, t128 = cdiv(n_out, 128) * row_tiles;
+    const long c256 = cdiv(t256, sms) * 256, c128 = cdiv(t128, sms) * 128;
+    return (c128 < c256) ? 128 : 256;
 }
 
 }  // namespace
@@ -450,14 +468,14 @@ using namespace dfold;
 // C ABI
 // ---------------------------------------------------------------------------------------------------
 extern "C" int dfold_gemm_bf16x3(
-    const uint16_t* a_hi, const uint16_t* a_lo, long F, long Nr, long K, long lda,
+    const uint16_t* a_hi, const uint16_t* a_lo, long F, long F_out, int f_start, long Nr, long K, long lda,
     const uint16_t* b_hi, const uint16_t* b_lo, long n_out, long ldb, int taps_f, int taps_n,
     float* out, long ldo, const float* bias, const float* residual, long ldr,
     float alpha, float beta, int act, void* stream) {
-    DFOLD_REQUIRE(F > 0 && Nr > 0 && K > 0 && n_out > 0, "dfold_gemm_bf16x3: empty problem");
+    DFOLD_REQUIRE(F > 0 && F_out > 0 && Nr > 0 && K > 0 && n_out > 0, "dfold_gemm_bf16x3: empty problem");
     DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dfold_gemm_bf16x3: lda/ldb must be multiples of 8 (got %ld, %ld)", lda, ldb);
     DFOLD_REQUIRE(taps_f >= 1 && taps_n >= 1 && (taps_f & 1) && (taps_n & 1), "dfold_gemm_bf16x3: tap grid must be odd");
-    const int bn = pick_bn(n_out);
+    const int bn = pick_bn(n_out, F_out * cdiv(Nr, BM));
     CUtensorMap maps[4];
     // A: dims (K, Nr, F)   B: dims (K, n_out, taps)
     if (make_map(&maps[0], a_hi, K, Nr, F, lda, Nr * lda, BK, BM, 1)) return 1;
@@ -472,13 +490,14 @@ extern "C" int dfold_gemm_bf16x3(
     p.taps_n = taps_n; p.taps_f = taps_f;
     p.tiles_per_frame = (int)cdiv(Nr, BM);
     p.Nr = (int)Nr;
-    p.out_rows = F * Nr;
+    p.out_rows = F_out * Nr;
     p.n_out = (int)n_out;
     p.out = out; p.ldo = ldo; p.out_tap_stride = 0;
     p.bias = bias; p.res = residual; p.ldr = ldr;
     p.alpha = alpha; p.beta = beta; p.act = act;
     default_batching(p);
-    dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(F * p.tiles_per_frame), 1);
+    p.f_start = f_start;
+    dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(F_out * p.tiles_per_frame), 1);
     cudaStream_t st = as_stream(stream);
     if (bn == 256) return launch<256>(maps, p, grid, st);
     if (bn == 128) return launch<128>(maps, p, grid, st);
@@ -486,22 +505,23 @@ extern "C" int dfold_gemm_bf16x3(
 }
 
 // out[tap][m][n] = alpha * sum_{f, j} A[f][j][m] * B[f + df(tap)][j + dn(tap)][n]      (weight gradient; K = pixels)
-// A planes [F][Nr][lda] (e.g. the gated output gradient, m = output channel), B planes [F][Nr][ldb] (the layer input,
-// n = input channel): the SAME pixel-major planes the forward / data-gradient GEMMs use, read MN-major.
+// A planes [F][Nr][lda] (e.g. the gated output gradient, m = output channel), B planes [Fb][Nr][ldb] (the layer input,
+// n = input channel, frame f of A pairs with frame f + b_f_add of B: cropped convolutions): the SAME pixel-major
+// planes the forward / data-gradient GEMMs use, read MN-major.
 extern "C" int dfold_gemm_wgrad_bf16x3(
     const uint16_t* a_hi, const uint16_t* a_lo, long M, long lda,
     const uint16_t* b_hi, const uint16_t* b_lo, long Nn, long ldb,
-    long F, long Nr, int taps_f, int taps_n,
+    long F, long Fb, int b_f_add, long Nr, int taps_f, int taps_n,
     float* out, long ldo, float alpha, void* stream) {
-    DFOLD_REQUIRE(M > 0 && Nn > 0 && F > 0 && Nr > 0, "dfold_gemm_wgrad_bf16x3: empty problem");
+    DFOLD_REQUIRE(M > 0 && Nn > 0 && F > 0 && Fb > 0 && Nr > 0, "dfold_gemm_wgrad_bf16x3: empty problem");
     DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dfold_gemm_wgrad_bf16x3: lda/ldb must be multiples of 8 (got %ld, %ld)", lda, ldb);
-    const int bn = pick_bn(Nn);
+    const int bn = pick_bn(Nn, cdiv(M, BM) * taps_f * taps_n);
     CUtensorMap maps[4];
     // dims (channel, residue, frame); boxes of 64 channels x 64 residues
     if (make_map(&maps[0], a_hi, M, Nr, F, lda, Nr * lda, 64, BK, 1)) return 1;
     if (make_map(&maps[1], a_lo, M, Nr, F, lda, Nr * lda, 64, BK, 1)) return 1;
-    if (make_map(&maps[2], b_hi, Nn, Nr, F, ldb, Nr * ldb, 64, BK, 1)) return 1;
-    if (make_map(&maps[3], b_lo, Nn, Nr, F, ldb, Nr * ldb, 64, BK, 1)) return 1;
+    if (make_map(&maps[2], b_hi, Nn, Nr, Fb, ldb, Nr * ldb, 64, BK, 1)) return 1;
+    if (make_map(&maps[3], b_lo, Nn, Nr, Fb, ldb, Nr * ldb, 64, BK, 1)) return 1;
     GemmParams p{};
     p.mode = 1;
     p.kc = (int)cdiv(Nr, BK);
@@ -513,6 +533,7 @@ extern "C" int dfold_gemm_wgrad_bf16x3(
     p.bias = nullptr; p.res = nullptr; p.ldr = 0;
     p.alpha = alpha; p.beta = 0.f; p.act = 0;
     default_batching(p);
+    p.b_f_add = b_f_add;
     dim3 grid((unsigned)cdiv(Nn, bn), (unsigned)cdiv(M, BM), (unsigned)(taps_f * taps_n));
     cudaStream_t st = as_stream(stream);
     if (bn == 256) return launch<256>(maps, p, grid, st);
@@ -534,7 +555,7 @@ extern "C" int dfold_gemm_bf16x3_batched(
     DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dfold_gemm_bf16x3_batched: lda/ldb must be multiples of 8");
     DFOLD_REQUIRE(a_k_bstride % 8 == 0 && b_k_ofs % 8 == 0 && b_k_bstride % 8 == 0,
                   "dfold_gemm_bf16x3_batched: K offsets must be multiples of 8 elements (TMA 16-byte alignment)");
-    const int bn = pick_bn(n_out);
+    const int bn = pick_bn(n_out, n_batches * cdiv(Nr, BM));
     CUtensorMap maps[4];
     if (make_map(&maps[0], a_hi, a_cols, Nr, a_frames, lda, Nr * lda, BK, BM, 1)) return 1;
     if (make_map(&maps[1], a_lo, a_cols, Nr, a_frames, lda, Nr * lda, BK, BM, 1)) return 1;
@@ -577,7 +598,7 @@ extern "C" int dfold_gemm_wgrad_bf16x3_batched(
     DFOLD_REQUIRE(M > 0 && Nn > 0 && Fk > 0 && Nr > 0 && zcount > 0 && splits > 0, "dfold_gemm_wgrad_bf16x3_batched: empty problem");
     DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && a_ostride % 8 == 0 && b_ostride % 8 == 0 && b_n_zmul % 8 == 0,
                   "dfold_gemm_wgrad_bf16x3_batched: strides / offsets must be multiples of 8 elements");
-    const int bn = pick_bn(Nn);
+    const int bn = pick_bn(Nn, cdiv(M, BM) * zcount * splits);
     CUtensorMap maps[4];
     if (make_map(&maps[0], a_hi, M, a_mid, a_outer, lda, a_ostride, 64, BK, 1)) return 1;
     if (make_map(&maps[1], a_lo, M, a_mid, a_outer, lda, a_ostride, 64, BK, 1)) return 1;

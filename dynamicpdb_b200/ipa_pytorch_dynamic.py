@@ -196,12 +196,19 @@ class ConvNet(nn.Module):
                 nn.Conv2d(dim, dim // 2, kernel_size=5, padding=2), nn.ReLU(True),
                 nn.Conv2d(dim // 2, dim, kernel_size=5, padding=2), nn.ReLU(True)))
 
-    def forward(self, x):
-        """x [frames, residues, dim] -> same shape."""
+    def forward(self, x, last_frame_only: bool = False):
+        """x [frames, residues, dim] -> same shape.
+
+        ``last_frame_only`` (needs >= 17 frames): returns [1, residues, dim], the LAST frame of the full result, computing
+        for each of the eight layers only the frames that last frame still depends on (15, 13, ... 1)."""
         for st in range(1, 5):
             seq = getattr(self, f"conv{st}")
-            h = K.conv5x5(x, seq[0].weight, seq[0].bias, relu=True)
-            x = K.conv5x5(h, seq[2].weight, seq[2].bias, relu=True, residual=x)
+            if last_frame_only:
+                h = K.conv5x5(x, seq[0].weight, seq[0].bias, relu=True, crop=2)
+                x = K.conv5x5(h, seq[2].weight, seq[2].bias, relu=True, residual=x[4:], crop=2)
+            else:
+                h = K.conv5x5(x, seq[0].weight, seq[0].bias, relu=True)
+                x = K.conv5x5(h, seq[2].weight, seq[2].bias, relu=True, residual=x)
         return x
 
 
@@ -340,10 +347,14 @@ class DFOLDIpaScore(nn.Module):
             # (ref :869), block 0's features feed AngleResnet.s_initial (:875-878) and the last block's feed
             # AngleResnet (:878); for the blocks in between, every other frame of the ConvNet output is dead.
             # Eight 5x5 convolutions reach 8*2 = 16 frames back, so the last 17 input frames reproduce the last
-            # output frame exactly (the cropped edge's zero padding cannot reach it).
+            # output frame exactly (the cropped edge's zero padding cannot reach it), and layer k of the stack only
+            # needs to produce the 17 - 2k frames the last one still depends on.
             halo = 2 * 8
             middle = (0 < b < self._ipa_conf.num_blocks - 1) and nf > halo + 1 and _DEAD_FRAME_SKIP
-            node_feat = self.trunk["conv_0"](node_feat[-(halo + 1):] if middle else node_feat)
+            if middle:
+                node_feat = self.trunk["conv_0"](node_feat[-(halo + 1):], last_frame_only=True)     # [1,N,5c]
+            else:
+                node_feat = self.trunk["conv_0"](node_feat)
 
             upd_last = self.trunk[f"bb_update_{b}"](node_feat[-1:])        # [1,N,6]
             rigid_update = torch.cat([upd_last.new_zeros((nf - 1,) + upd_last.shape[1:]), upd_last], dim=0)   # ref :869

@@ -37,8 +37,8 @@ _SIGS = {
     "dfold_rigid_apply_bwd": "ppplp" + "ppp" + "lliip",
     "dfold_compose_q_update_fwd": "pppppplp",
     "dfold_compose_q_update_bwd": "pppppppplp",
-    "dfold_gemm_bf16x3": "ppllll" + "ppllii" + "pl" + "p" + "pl" + "ffi" + "p",
-    "dfold_gemm_wgrad_bf16x3": "ppll" + "ppll" + "llii" + "plf" + "p",
+    "dfold_gemm_bf16x3": "pplli" + "lll" + "ppllii" + "pl" + "p" + "pl" + "ffi" + "p",
+    "dfold_gemm_wgrad_bf16x3": "ppll" + "ppll" + "llilii" + "plf" + "p",
     "dfold_ipa_attn_fwd": "plplppplpppp" + "iiiiiiii" + "ff" + "ppp",
     "dfold_ipa_attn_bwd": "plplppplpppp" + "iiiiiiii" + "ff" + "ppp" + "ppppppppp" + "p",
     "dfold_ipa_pre_bwd": "pp" + "iiiiiii" + "pp" + "pppp" + "p",
@@ -214,24 +214,29 @@ def _conv_planes(w: torch.Tensor):
     return _cache_get("conv", w, build)
 
 
-def _gemm(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act):
-    with _timed("gemm_bf16x3", 2.0 * F * Nr * K * n_out * taps_f * taps_n):
-        _gemm_launch(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act)
+def _gemm(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act,
+          F_out=None, f_start=0):
+    F_out = F if F_out is None else F_out
+    with _timed("gemm_bf16x3", 2.0 * F_out * Nr * K * n_out * taps_f * taps_n):
+        _gemm_launch(a_hi, a_lo, F, F_out, f_start, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr,
+                     alpha, beta, act)
 
 
-def _gemm_launch(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act):
-    _check(lib().dfold_gemm_bf16x3(_ptr(a_hi), _ptr(a_lo), F, Nr, K, lda, _ptr(b_hi), _ptr(b_lo), n_out, ldb, taps_f, taps_n,
+def _gemm_launch(a_hi, a_lo, F, F_out, f_start, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr,
+                 alpha, beta, act):
+    _check(lib().dfold_gemm_bf16x3(_ptr(a_hi), _ptr(a_lo), F, F_out, f_start, Nr, K, lda, _ptr(b_hi), _ptr(b_lo), n_out, ldb, taps_f, taps_n,
                                    _ptr(out), ldo, _ptr(bias), _ptr(residual), ldr, alpha, beta, act, _stream()),
            "dfold_gemm_bf16x3")
 
 
-def _gemm_wgrad(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo):
+def _gemm_wgrad(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo, Fb=None, b_f_add=0):
+    Fb = F if Fb is None else Fb
     with _timed("gemm_bf16x3", 2.0 * F * Nr * M * Nn * taps_f * taps_n):
-        _gemm_wgrad_launch(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo)
+        _gemm_wgrad_launch(a, M, lda, b, Nn, ldb, F, Fb, b_f_add, Nr, taps_f, taps_n, out, ldo)
 
 
-def _gemm_wgrad_launch(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo):
-    _check(lib().dfold_gemm_wgrad_bf16x3(_ptr(a[0]), _ptr(a[1]), M, lda, _ptr(b[0]), _ptr(b[1]), Nn, ldb, F, Nr, taps_f, taps_n,
+def _gemm_wgrad_launch(a, M, lda, b, Nn, ldb, F, Fb, b_f_add, Nr, taps_f, taps_n, out, ldo):
+    _check(lib().dfold_gemm_wgrad_bf16x3(_ptr(a[0]), _ptr(a[1]), M, lda, _ptr(b[0]), _ptr(b[1]), Nn, ldb, F, Fb, b_f_add, Nr, taps_f, taps_n,
                                          _ptr(out), ldo, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3")
 
 
@@ -259,6 +264,7 @@ class _LinearFn(Function):
         r2 = _f32c(residual.reshape(-1, N_)) if residual is not None else None
         out = torch.empty((M_, N_), dtype=torch.float32, device=x.device)
         tc = _use_tensor_cores(M_, N_, K_)
+        a_hi = a_lo = None
         if tc:
             (a_hi, a_lo), _ = _split2d(x2, pre_relu=pre_relu)
             w_hi, w_lo, _, _ = _linear_planes(w)
@@ -266,15 +272,17 @@ class _LinearFn(Function):
         else:
             _sgemm(x2, 0, K_, 1, 0, 0, wf, 0, K_, 1, 0, 0, out, 0, N_, 1, 0, 0, M_, N_, K_, R=r2, r_rs=N_, r_cs=1,
                    bias=bf, act=_ACT[act], pre_relu=int(pre_relu))
-        ctx.save_for_backward(x2, w, out if act == "relu" else None, r2 if act == "relu" else None)
+        # the tensor-core path keeps the bf16 operand planes (same bytes as x) for the weight gradient instead of x
+        ctx.save_for_backward(None if tc else x2, w, out if act == "relu" else None, r2 if act == "relu" else None, a_hi, a_lo)
+        ctx.mk = (M_, K_)
         ctx.meta = (x.shape, act, pre_relu, tc, b is not None, residual is not None and residual.shape)
         return out.reshape(x.shape[:-1] + (N_,))
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w, out, r2 = ctx.saved_tensors
+        x2, w, out, r2, a_hi, a_lo = ctx.saved_tensors
         xshape, act, pre_relu, tc, has_b, rshape = ctx.meta
-        M_, K_ = x2.shape
+        M_, K_ = ctx.mk
         N_ = w.shape[0]
         g = _f32c(dy.reshape(M_, N_))
         gate = None
@@ -292,9 +300,8 @@ class _LinearFn(Function):
                 dx = torch.empty((M_, K_), dtype=torch.float32, device=g.device)
                 _gemm(g_hi, g_lo, 1, M_, N_, g_hi.shape[1], wt_hi, wt_lo, K_, wt_hi.shape[1], 1, 1, dx, K_, None, None, 0, 1.0, 0.0, 0)
             if need_w:
-                (x_hi, x_lo), _ = _split2d(x2, pre_relu=pre_relu)
                 dw = torch.empty((N_, K_), dtype=torch.float32, device=g.device)
-                _gemm_wgrad((g_hi, g_lo), N_, g_hi.shape[1], (x_hi, x_lo), K_, x_hi.shape[1], 1, M_, 1, 1, dw, K_)
+                _gemm_wgrad((g_hi, g_lo), N_, g_hi.shape[1], (a_hi, a_lo), K_, a_hi.shape[1], 1, M_, 1, 1, dw, K_)
         else:
             if gate is not None:
                 g = g * (gate > 0)
@@ -313,7 +320,8 @@ class _LinearFn(Function):
                 db = g.sum(0)
         if dx is not None:
             if pre_relu:
-                dx = dx * (x2 > 0)
+                # relu(x) > 0  <=>  its bf16 hi plane is a positive number
+                dx = dx * ((x2 > 0) if x2 is not None else (a_hi[:, :K_] > 0))
             dx = dx.reshape(xshape)
         return dx, dw, db, None, dres, None
 
@@ -331,29 +339,33 @@ def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, pre_r
 # --------------------------------------------------------------------------------------------------
 class _Conv5x5Fn(Function):
     @staticmethod
-    def forward(ctx, x, w, b, relu, residual):
+    def forward(ctx, x, w, b, relu, residual, crop):
         _need_cuda(x, w, b, residual)
         F_, N_, Ci = x.shape
         Co, Ci2, kh, kw = w.shape
         if Ci2 != Ci or Ci % 8 or Co % 8:
             raise ValueError(f"conv5x5: channels must match and be multiples of 8 (got {Ci}->{Co})")
+        Fo = F_ - crop                                   # only the last Fo frames are produced
+        if Fo < 1:
+            raise ValueError("conv5x5: crop removes every frame")
         x2 = _f32c(x.reshape(F_ * N_, Ci))
-        r2 = _f32c(residual.reshape(F_ * N_, Co)) if residual is not None else None
-        out = torch.empty((F_ * N_, Co), dtype=torch.float32, device=x.device)
+        r2 = _f32c(residual.reshape(Fo * N_, Co)) if residual is not None else None
+        out = torch.empty((Fo * N_, Co), dtype=torch.float32, device=x.device)
         (a_hi, a_lo), _ = _split2d(x2)
         f_hi, f_lo, _, _ = _conv_planes(w)
         _gemm(a_hi, a_lo, F_, N_, Ci, Ci, f_hi, f_lo, Co, f_hi.shape[2], kh, kw, out, Co, _f32c(b) if b is not None else None,
-              r2, Co, 1.0, 1.0, 1 if relu else 0)
-        ctx.save_for_backward(x2, w, out if relu else None, r2 if relu else None)
-        ctx.meta = (x.shape, relu, b is not None, residual is not None)
-        return out.reshape(F_, N_, Co)
+              r2, Co, 1.0, 1.0, 1 if relu else 0, F_out=Fo, f_start=crop)
+        ctx.save_for_backward(a_hi, a_lo, w, out if relu else None, r2 if relu else None)
+        ctx.meta = (x.shape, relu, b is not None, residual is not None, crop)
+        return out.reshape(Fo, N_, Co)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w, out, r2 = ctx.saved_tensors
-        (F_, N_, Ci), relu, has_b, has_r = ctx.meta
+        x_hi, x_lo, w, out, r2 = ctx.saved_tensors
+        (F_, N_, Ci), relu, has_b, has_r, crop = ctx.meta
         Co, _, kh, kw = w.shape
-        g = _f32c(dy.reshape(F_ * N_, Co))
+        Fo = F_ - crop
+        g = _f32c(dy.reshape(Fo * N_, Co))
         gate = None
         if relu:
             gate = out if r2 is None else (out - r2)
@@ -365,21 +377,22 @@ class _Conv5x5Fn(Function):
         if need_x:
             _, _, d_hi, d_lo = _conv_planes(w)
             dx = torch.empty((F_ * N_, Ci), dtype=torch.float32, device=g.device)
-            _gemm(g_hi, g_lo, F_, N_, Co, Co, d_hi, d_lo, Ci, d_hi.shape[2], kh, kw, dx, Ci, None, None, 0, 1.0, 0.0, 0)
+            _gemm(g_hi, g_lo, Fo, N_, Co, Co, d_hi, d_lo, Ci, d_hi.shape[2], kh, kw, dx, Ci, None, None, 0, 1.0, 0.0, 0,
+                  F_out=F_, f_start=-crop)
             dx = dx.reshape(F_, N_, Ci)
         if need_w:
-            (x_hi, x_lo), _ = _split2d(x2)
             taps = torch.empty((kh * kw, Co, Ci), dtype=torch.float32, device=g.device)
-            _gemm_wgrad((g_hi, g_lo), Co, Co, (x_hi, x_lo), Ci, Ci, F_, N_, kh, kw, taps, Ci)
+            _gemm_wgrad((g_hi, g_lo), Co, Co, (x_hi, x_lo), Ci, Ci, Fo, N_, kh, kw, taps, Ci, Fb=F_, b_f_add=crop)
             dw = torch.empty((Co, Ci, kh, kw), dtype=torch.float32, device=g.device)
             _check(lib().dfold_taps_to_param(_ptr(taps), Co, Ci, kh * kw, _ptr(dw), _stream()), "dfold_taps_to_param")
-        return dx, dw, db, None, (dy if has_r else None)
+        return dx, dw, db, None, (dy if has_r else None), None
 
 
-def conv5x5(x, weight, bias=None, relu: bool = True, residual=None):
+def conv5x5(x, weight, bias=None, relu: bool = True, residual=None, crop: int = 0):
     """Channels-last ``Conv2d(kernel 5, padding 2)`` over the (frame, residue) image: x [F, N, C_in] ->
-    ``relu?(conv(x) + bias) + residual`` [F, N, C_out]; weight keeps the reference's [C_out, C_in, 5, 5] layout."""
-    return _Conv5x5Fn.apply(x, weight, bias, relu, residual)
+    ``relu?(conv(x) + bias) + residual`` [F, N, C_out]; weight keeps the reference's [C_out, C_in, 5, 5] layout.
+    ``crop > 0`` produces only the last ``F - crop`` output frames (residual must have that many frames)."""
+    return _Conv5x5Fn.apply(x, weight, bias, relu, residual, crop)
 
 
 # --------------------------------------------------------------------------------------------------

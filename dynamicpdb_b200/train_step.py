@@ -39,11 +39,16 @@ class TrainStep:
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_error: Optional[str] = None
+        import os, sys, time
+        verbose = os.environ.get("DFOLD_BENCH_VERBOSE", "0") == "1"
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(max(1, warmup)):
+            for it in range(max(1, warmup)):
                 self._eager()
+                if verbose:
+                    torch.cuda.synchronize()
+                    print(f"[train_step t={time.perf_counter():.1f}] eager warm-up step {it} done", file=sys.stderr, flush=True)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if graph:

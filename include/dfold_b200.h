@@ -47,22 +47,24 @@ int dfold_conv_weight_prep(const float* w, int O, int I, int T, uint16_t* f_hi, 
 /* g[T][O][I] -> out[O][I][T]: weight gradient back to the parameter layout. */
 int dfold_taps_to_param(const float* g, int O, int I, int T, float* out, void* stream);
 
-/* out[f*Nr + n, c] = act(alpha * sum_{tf,tn,k} A[f + tf - taps_f/2, n + tn - taps_n/2, k] * B[tf*taps_n+tn][c][k]
+/* for f in [0, F_out):
+ * out[f*Nr + n, c] = act(alpha * sum_{tf,tn,k} A[f + f_start + tf - taps_f/2, n + tn - taps_n/2, k] * B[tf*taps_n+tn][c][k]
  *                        + bias[c]) + beta * residual[f*Nr + n, c]
  * A planes [F][Nr][lda] (zero outside the image: the 5x5 halo is a TMA out-of-bounds fill), B planes
  * [taps][n_out][ldb].  taps_f = taps_n = 1 is a plain linear layer (x @ W^T).  act: 0 none, 1 ReLU, 2 SiLU.
- * lda, ldb multiples of 8.  bias / residual nullable. */
-int dfold_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, long F, long Nr, long K, long lda,
+ * lda, ldb multiples of 8.  bias / residual nullable.  F_out = F, f_start = 0 is the plain convolution; F_out < F with
+ * f_start = F - F_out computes only the last F_out frames (dead-frame pyramid), f_start < 0 is its data gradient. */
+int dfold_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, long F, long F_out, int f_start, long Nr, long K, long lda,
                       const uint16_t* b_hi, const uint16_t* b_lo, long n_out, long ldb, int taps_f, int taps_n,
                       float* out, long ldo, const float* bias, const float* residual, long ldr,
                       float alpha, float beta, int act, void* stream);
 
-/* Weight gradient: out[t][m][n] = alpha * sum_{f,j} A[f][j][m] * B[f + tf - taps_f/2][j + tn - taps_n/2][n]
- * A planes [F][Nr][lda] (gated output gradient, m = output channel), B planes [F][Nr][ldb] (layer input,
+/* Weight gradient: out[t][m][n] = alpha * sum_{f,j} A[f][j][m] * B[f + b_f_add + tf - taps_f/2][j + tn - taps_n/2][n]
+ * A planes [F][Nr][lda] (gated output gradient, m = output channel), B planes [Fb][Nr][ldb] (layer input,
  * n = input channel) — the same pixel-major planes as above, consumed MN-major by the tensor core; out [taps][M][ldo]. */
 int dfold_gemm_wgrad_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, long M, long lda,
                             const uint16_t* b_hi, const uint16_t* b_lo, long Nn, long ldb,
-                            long F, long Nr, int taps_f, int taps_n,
+                            long F, long Fb, int b_f_add, long Nr, int taps_f, int taps_n,
                             float* out, long ldo, float alpha, void* stream);
 
 /* Batched K-major GEMM (no taps).  For every row tile of "frame" b in [0, n_batches), hb = b % bmod:

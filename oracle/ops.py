@@ -22,9 +22,9 @@ def linear(x, weight, bias=None, act=None, residual=None, pre_relu=False):
     return y if residual is None else y + residual
 
 
-def conv5x5(x, weight, bias=None, relu=True, residual=None):
+def conv5x5(x, weight, bias=None, relu=True, residual=None, crop=0):
     y = F.conv2d(x.permute(2, 0, 1).unsqueeze(0), weight, bias, padding=(weight.shape[2] // 2, weight.shape[3] // 2))
-    y = y.squeeze(0).permute(1, 2, 0)
+    y = y.squeeze(0).permute(1, 2, 0)[crop:]
     if relu:
         y = F.relu(y)
     return y if residual is None else y + residual

@@ -180,3 +180,12 @@ def test_ipa_attention(F, N, H, C, Pq, Pv, Cp, Fs, Fz, dfold, masked):
     # quantises the logits to 2^-7, so those rows are compared only through the unmasked ones
     post = lambda out, *a: out * a[7][:, :, None]
     check("ipa_attention", inputs, 2e-4, post=post, Pq=Pq, Pv=Pv, dfold=dfold, inf=1e5, eps=1e-8)
+
+
+@pytest.mark.parametrize("F,N,Ci,Co,crop", [(7, 24, 64, 128, 2), (17, 40, 160, 80, 2), (5, 130, 128, 64, 4)])
+@pytest.mark.parametrize("relu,res", [(True, True), (False, False)])
+def test_conv5x5_cropped(F, N, Ci, Co, crop, relu, res):
+    """Only the last F - crop output frames (dead-frame pyramid): forward, data gradient and weight gradient."""
+    inputs = [R(F, N, Ci), R(Co, Ci, 5, 5, scale=1.0 / math.sqrt(25 * Ci)), R(Co)]
+    residual = R(F - crop, N, Co) if res else None
+    check("conv5x5", inputs, 1e-4, outliers=(60 * max(Ci, Co) if relu else 0), relu=relu, residual=residual, crop=crop)
