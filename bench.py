@@ -129,7 +129,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -283,7 +283,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_ipa": roof_ipa, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     _finish(world, dist)
 
 
@@ -292,6 +292,7 @@ def _finish(world, dist):
     still references the communicator.  Every rank has finished measuring (the timed regions end with barriers)."""
     sys.stdout.flush()
     sys.stderr.flush()
+    _REAL_STDOUT.flush()
     if world > 1:
         try:
             dist.barrier()
@@ -301,7 +302,17 @@ def _finish(world, dist):
         os._exit(0)
 
 
+def _json_only_stdout():
+    """Library banners (e.g. NCCL's version line) go to fd 1; keep fd 1 for the ONE JSON line by pointing it at stderr
+    for the rest of the process and returning a private handle to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
+    _REAL_STDOUT = _json_only_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)
