@@ -177,3 +177,25 @@ def test_dead_frame_elimination_is_exact(oracle_ops, monkeypatch):
     for k in res[False][1]:
         a, b = res[True][1][k], res[False][1][k]
         assert (a - b).norm() <= 1e-5 * (b.norm() + 1e-12), k
+
+
+def test_memoized_inference_matches_repeated_forward(oracle_ops):
+    """Trunk memoisation across reverse-diffusion steps (only t / rigids_t change) reproduces the full forward."""
+    from dynamicpdb_b200.inference import MemoizedScoreNetwork
+    nf, N = 3, 10
+    torch.manual_seed(0)
+    net = FullScoreNetwork(syn.model_conf(nf, **syn.PRESET_TINY), SE3ScoreDiffuser(syn.diffuser_conf(1.0)))
+    sd = net.state_dict()
+    syn.dezero_(sd)
+    net.load_state_dict(sd)
+    memo = MemoizedScoreNetwork(net)
+    feats = syn.make_feats(nf, N, seed=6)
+    for step, tval in enumerate((1.0, 0.6, 0.05)):
+        feats = dict(feats)
+        feats["t"] = torch.tensor([tval])
+        feats["rigids_t"] = syn.make_feats(nf, N, seed=100 + step)["rigids_t"]
+        with torch.no_grad():
+            full = net(dict(feats))
+        fast = memo(dict(feats))
+        for k in full:
+            assert close(fast[k], full[k], 1e-6), (step, k)
