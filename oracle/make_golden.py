@@ -125,7 +125,33 @@ def run_rigid():
     print("rigid ok")
 
 
+def run_transitions():
+    """§8 row a15: the transition modules the fork defines (ipa_pytorch_dynamic.py:175-239, 519-572)."""
+    from src.model import ipa_pytorch_dynamic as RefIpa
+    g = torch.Generator().manual_seed(41)
+    c, B, N, cz = 32, 2, 9, 16
+    s = torch.randn(B, N, c, generator=g)
+    e = torch.randn(B, N, N, cz, generator=g)
+    mods = {
+        "sm_transition": RefIpa.StructureModuleTransition(c),
+        "edge_transition": RefIpa.EdgeTransition(node_embed_size=c, edge_embed_in=cz, edge_embed_out=cz),
+        "torsion_angles": RefIpa.TorsionAngles(c, 7),
+        "score_layer": RefIpa.ScoreLayer(c, c, 6),
+    }
+    out = {"dims": dict(c=c, B=B, N=N, cz=cz)}
+    for i, (k, m) in enumerate(mods.items()):
+        sd = syn.random_state({n: v.shape for n, v in m.state_dict().items()}, seed=50 + i)
+        m.load_state_dict(sd)
+        out[k + "_shapes"] = {n: tuple(v.shape) for n, v in sd.items()}
+        with torch.no_grad():
+            y = m(s, e) if k == "edge_transition" else m(s)
+        out[k] = [t.detach() for t in y] if isinstance(y, tuple) else y.detach()
+    torch.save(out, os.path.join(OUT, "transitions.pt"))
+    print("transitions ok")
+
+
 if __name__ == "__main__":
+    run_transitions()
     for n, c in NET_CASES.items():
         run_net(n, c)
     run_vanilla()

@@ -199,3 +199,34 @@ def test_memoized_inference_matches_repeated_forward(oracle_ops):
         fast = memo(dict(feats))
         for k in full:
             assert close(fast[k], full[k], 1e-6), (step, k)
+
+
+def test_transition_modules_match_reference_golden(oracle_ops):
+    """StructureModuleTransition / EdgeTransition / TorsionAngles / ScoreLayer of the fork."""
+    from dynamicpdb_b200 import ipa_pytorch_dynamic as ipd
+    from oracle import dfold_oracle as O
+    g = load("transitions")
+    d = g["dims"]
+    gen = torch.Generator().manual_seed(41)
+    s = torch.randn(d["B"], d["N"], d["c"], generator=gen)
+    e = torch.randn(d["B"], d["N"], d["N"], d["cz"], generator=gen)
+    mods = {
+        "sm_transition": ipd.StructureModuleTransition(d["c"]),
+        "edge_transition": ipd.EdgeTransition(node_embed_size=d["c"], edge_embed_in=d["cz"], edge_embed_out=d["cz"]),
+        "torsion_angles": ipd.TorsionAngles(d["c"], 7),
+        "score_layer": ipd.ScoreLayer(d["c"], d["c"], 6),
+    }
+    for i, (k, m) in enumerate(mods.items()):
+        sd = syn.random_state(g[k + "_shapes"], seed=50 + i)
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            y = m(s, e) if k == "edge_transition" else m(s)
+        ys = list(y) if isinstance(y, tuple) else [y]
+        refs = g[k] if isinstance(g[k], list) else [g[k]]
+        for a, b in zip(ys, refs):
+            assert close(a, b, 2e-5), k
+        # the oracle restatement of the same modules
+        if k == "sm_transition":
+            assert close(O.sm_transition({"m." + n: v for n, v in sd.items()}, "m", s), g[k], 2e-5)
+        if k == "edge_transition":
+            assert close(O.edge_transition({"m." + n: v for n, v in sd.items()}, "m", s, e), g[k], 2e-5)
