@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-literal", action="store_true", help="skip the extra measurement with dead-frame elimination off")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames in the bounded CPU sample")
     return ap.parse_args()
 
@@ -224,6 +225,24 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches = K.LAUNCH_COUNT // prof_steps
     prof, K.PROFILE = K.PROFILE, None
+
+    # transparency: the same step with the reference's literal schedule (ConvNet on every frame in every block,
+    # i.e. dead-frame elimination off) — every rank takes part (the step contains the gradient all-reduce)
+    literal = None
+    if not args.no_literal:
+        try:
+            from dynamicpdb_b200 import ipa_pytorch_dynamic as ipd
+            if ipd._DEAD_FRAME_SKIP:
+                ipd._DEAD_FRAME_SKIP = False
+                ts_main, ts = ts, None
+                ts = TrainStep(net, syn.surrogate_loss, resident, lr=1e-4, world_size=world, graph=not args.no_graph, warmup=2)
+                ms_lit = timed(max(2, min(3, args.steps)), e2e=False)
+                literal = {"value": world * nf / (ms_lit * 1e-3), "unit": "frames/s", "ms_per_step": ms_lit,
+                           "note": "DFOLD_NO_DEAD_FRAME_SKIP=1 schedule: all 64 frames through the ConvNet in all 4 blocks"}
+                ts = ts_main
+                ipd._DEAD_FRAME_SKIP = True
+        except Exception as e:      # noqa: BLE001
+            literal = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
     if rank != 0:
         _finish(world, dist)
         return
@@ -282,6 +301,7 @@ def run_ours(args):
         "e2e": {"value": world * nf / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_ipa": roof_ipa, "cpu_baseline": cpu,
+        "literal_schedule": literal,
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     _finish(world, dist)
