@@ -87,6 +87,11 @@ def cpu_oracle_fps(frames, n_res, steps, warmup):
     `frames` frames x `n_res` residues, all torch intra-op threads."""
     from dynamicpdb_b200 import synthetic as syn
     from oracle import dfold_oracle as O
+    # all host cores of this process (torchrun exports OMP_NUM_THREADS=1; the other ranks are idle in this leg)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:       # noqa: BLE001
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
     conf = syn.model_conf(frames, **syn.PRESET_A)
     from dynamicpdb_b200.Dfold_network_dynamic import FullScoreNetwork
@@ -116,9 +121,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
     frames = args.cpu_frames
     fps, ms = cpu_oracle_fps(frames, args.res, args.steps, args.warmup)
+    cores = torch.get_num_threads()
     sample = f"one window of {frames} frames x {args.res} residues per step (per-frame cost is linear in the frame count)"
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -284,8 +289,8 @@ def run_ours(args):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cores = torch.get_num_threads()
         fps, cms = cpu_oracle_fps(args.cpu_frames, N, 1, 1)
+        cores = torch.get_num_threads()
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": f"one fwd+bwd of {args.cpu_frames} frames x {N} residues ({cms / 1e3:.1f} s), oracle/dfold_oracle.py"}
 
