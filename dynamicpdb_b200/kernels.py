@@ -173,20 +173,30 @@ def _split2d(x2: torch.Tensor, *, pre_relu=False, gate=None, want=True, want_t=F
 
 
 _WCACHE = {}
+_WCACHE_EPOCH = 0
+
+
+def invalidate_weight_cache():
+    """Forget every cached weight plane.  A CUDA-graph replay updates the weights on the device without bumping the
+    Python-side version counters, so ``train_step.TrainStep`` calls this after each replay; the next EAGER call then
+    rebuilds its planes from the current weights (replays themselves never consult this cache)."""
+    global _WCACHE_EPOCH
+    _WCACHE_EPOCH += 1
 
 
 def _cache_get(kind, w: torch.Tensor, build):
     """bf16 operand planes of a weight, rebuilt whenever the tensor object or its version counter changes
-    (optimizer steps and load_state_dict bump ``_version``)."""
+    (optimizer steps and load_state_dict bump ``_version``) or a graph replay may have changed it."""
     key = (kind, id(w))
     ent = _WCACHE.get(key)
-    if ent is not None and ent[0]() is w and ent[1] == (w._version, w.data_ptr()):
+    stamp = (w._version, w.data_ptr(), _WCACHE_EPOCH)
+    if ent is not None and ent[0]() is w and ent[1] == stamp:
         return ent[2]
     val = build()
     if len(_WCACHE) > 512:
         for k in [k for k, e in _WCACHE.items() if e[0]() is None]:
             del _WCACHE[k]
-    _WCACHE[key] = (weakref.ref(w), (w._version, w.data_ptr()), val)
+    _WCACHE[key] = (weakref.ref(w), stamp, val)
     return val
 
 

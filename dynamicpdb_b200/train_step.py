@@ -19,6 +19,8 @@ from typing import Callable, Dict, Optional
 import torch
 import torch.distributed as dist
 
+from . import kernels as _kernels
+
 
 class TrainStep:
     def __init__(self, net: torch.nn.Module, loss_fn: Callable[[Dict[str, torch.Tensor]], torch.Tensor],
@@ -81,6 +83,7 @@ class TrainStep:
     def __call__(self) -> torch.Tensor:
         if self.graph is not None:
             self.graph.replay()
+            _kernels.invalidate_weight_cache()      # the replay moved the weights without touching their version counters
         else:
             self._eager()
         return self.loss
