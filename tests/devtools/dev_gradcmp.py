@@ -1,7 +1,7 @@
 """Development probe: compare intermediate activations / gradients of the product on GPU (CUDA kernels) with the same
 module code running on CPU over the oracle ops."""
 import sys, os, copy
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from dynamicpdb_b200 import kernels as K, synthetic as syn
 from dynamicpdb_b200.Dfold_network_dynamic import FullScoreNetwork

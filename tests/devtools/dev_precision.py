@@ -1,6 +1,6 @@
 """Development probe: error of the split-bf16 GEMM vs K, and per-output errors of the full network vs the oracle."""
 import sys, os, math, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from dynamicpdb_b200 import kernels as K, synthetic as syn
 from dynamicpdb_b200.Dfold_network_dynamic import FullScoreNetwork

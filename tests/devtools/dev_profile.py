@@ -1,6 +1,6 @@
 """Development probe: per-kernel time breakdown of one training step with torch.profiler."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 from dynamicpdb_b200 import synthetic as syn
