@@ -23,6 +23,22 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute applies to the CURRENT device only (the reference trainer may put the model on any GPU of the
+// node): remember, per kernel, what has been configured on each device.
+struct SmemCfg { size_t bytes[64] = {}; };
+template <typename Kern>
+static inline int ensure_dyn_smem(Kern k, size_t bytes, SmemCfg& cfg, const char* name) {
+    if (bytes <= 48 * 1024) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    dev &= 63;
+    if (cfg.bytes[dev] >= bytes) return 0;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    DFOLD_REQUIRE(e == cudaSuccess, "%s: cannot reserve %zu B of dynamic shared memory: %s", name, bytes, cudaGetErrorString(e));
+    cfg.bytes[dev] = bytes;
+    return 0;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

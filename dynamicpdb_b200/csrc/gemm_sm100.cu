@@ -420,12 +420,8 @@ int make_map(CUtensorMap* m, const void* base, long d0, long d1, long d2, long s
 template <int BN>
 int launch(const CUtensorMap* maps, const GemmParams& p, dim3 grid, cudaStream_t st) {
     using Cfg = TileCfg<BN>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        DFOLD_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
-        configured = true;
-    }
+    static SmemCfg cfg;
+    if (ensure_dyn_smem(gemm_bf16x3_kernel<BN>, Cfg::kSmemBytes, cfg, "gemm_bf16x3_kernel")) return 1;
     gemm_bf16x3_kernel<BN><<<grid, NTHREADS, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p);
     return check_launch("gemm_bf16x3_kernel");
 }
@@ -438,13 +434,14 @@ void default_batching(GemmParams& p) {
 }
 
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+    static int n[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    dev &= 63;
+    if (n[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 // Tile width: every CTA owns one SM (192 KB of shared memory), so the launch runs in ceil(tiles / SMs) waves whose

@@ -526,12 +526,8 @@ extern "C" int dfold_ipa_attn_bwd(IPA_ARGS, const float* out_cat, const float* l
     if (check_launch("ipa_bwd_pre_kernel")) return 1;
     const int PQ3 = Pq * 3, PV3 = Pv * 3, CW = C + PV3;
     const size_t smem = sizeof(float) * (size_t)(B1_TI * PQ3 + TJ * (PQ3 + 1) + (CW + Cp) * B1_TI + TJ * (CW + 1));
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(ipa_bwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        DFOLD_REQUIRE(e == cudaSuccess, "ipa_bwd_row: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-        configured = smem;
-    }
+    static SmemCfg cfg;
+    if (ensure_dyn_smem(ipa_bwd_row_kernel, smem, cfg, "ipa_bwd_row_kernel")) return 1;
     dim3 grid((unsigned)cdiv(N, B1_TI), (unsigned)H, (unsigned)F);
     ipa_bwd_row_kernel<<<grid, 256, smem, st>>>(p, dcat, d_og, delta, Pm, dS, dgamma);
     if (check_launch("ipa_bwd_row_kernel")) return 1;

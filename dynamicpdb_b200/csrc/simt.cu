@@ -377,7 +377,19 @@ __global__ void row_ln_bwd_kernel(const float* __restrict__ x, const float* __re
 using namespace dfold;
 
 extern "C" const char* dfold_last_error(void) { return g_err; }
-extern "C" int dfold_abi_version(void) { return 1; }
+extern "C" int dfold_abi_version(void) { return 2; }
+
+// id of the CUDA-graph capture `stream` is recording into (0 when the stream is not capturing).  The host side keys
+// its cached operand planes on it: planes built inside one capture must never be reused by another graph.
+extern "C" int dfold_capture_id(void* stream, unsigned long long* id_out) {
+    DFOLD_REQUIRE(id_out != nullptr, "dfold_capture_id: null output");
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    cudaError_t e = cudaStreamGetCaptureInfo(as_stream(stream), &st, &id);
+    DFOLD_REQUIRE(e == cudaSuccess, "dfold_capture_id: %s", cudaGetErrorString(e));
+    *id_out = (st == cudaStreamCaptureStatusActive) ? id : 0ull;
+    return 0;
+}
 
 // hi/lo: [R][ldo], columns [C, cpad) zero-filled.  hi_t/lo_t: [C][ldt], columns [R, rpad) zero-filled.
 extern "C" int dfold_split2d(const float* x, long R, long C, long ld, int pre_relu, const float* gate, long ldg,
@@ -401,12 +413,8 @@ extern "C" int dfold_conv_weight_prep(const float* w, int O, int I, int T, uint1
     DFOLD_REQUIRE(ldi >= I && (d_hi == nullptr || ldo >= O), "dfold_conv_weight_prep: bad leading dims");
     dim3 grid((unsigned)cdiv(I, 32), (unsigned)cdiv(O, 32));
     const size_t smem = (size_t)32 * (32 * T + 1) * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(conv_weight_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        DFOLD_REQUIRE(e == cudaSuccess, "conv_weight_prep: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
+    static SmemCfg cfg;
+    if (ensure_dyn_smem(conv_weight_prep_kernel, smem, cfg, "conv_weight_prep_kernel")) return 1;
     conv_weight_prep_kernel<<<grid, 256, smem, as_stream(stream)>>>(w, O, I, T, f_hi, f_lo, ldi, d_hi, d_lo, ldo);
     return check_launch("conv_weight_prep_kernel");
 }

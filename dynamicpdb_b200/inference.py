@@ -25,9 +25,20 @@ class MemoizedScoreNetwork(torch.nn.Module):
         self.net = net
         self._key = None
         self._cached: Optional[Dict[str, torch.Tensor]] = None
+        self._held = None
 
     def _signature(self, feats):
-        return tuple((k, feats[k].data_ptr(), feats[k]._version, tuple(feats[k].shape)) for k in _TRUNK_KEYS if k in feats)
+        """Identity + version of every trunk input, and the versions of the weights.  The keyed tensors themselves are
+        kept alive in ``self._held`` for as long as the entry lives: the reference deep-copies the window before every
+        sampling run (train_DFOLD_dynamics.py:1442), and a freed block is handed out again at the same address with
+        version 0 — (data_ptr, version, shape) alone would then collide with different contents."""
+        ins = tuple((k, id(feats[k]), feats[k]._version) for k in _TRUNK_KEYS if k in feats)
+        wts = tuple((id(p), p._version) for p in self.net.parameters())
+        return ins, wts
+
+    def reset(self):
+        """Drop the cached trunk outputs (call after weight updates made through ``param.data``, which bump no version)."""
+        self._key, self._cached, self._held = None, None, None
 
     @torch.no_grad()
     def forward(self, input_feats, drop_ref=False):
@@ -35,6 +46,7 @@ class MemoizedScoreNetwork(torch.nn.Module):
         if self._cached is None or sig != self._key:
             self._cached = self.net(input_feats, drop_ref=drop_ref)
             self._key = sig
+            self._held = [input_feats[k] for k in _TRUNK_KEYS if k in input_feats]
             return dict(self._cached)
         out = dict(self._cached)
         diffuser = self.net.diffuser

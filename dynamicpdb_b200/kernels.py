@@ -9,6 +9,7 @@ torch is used for: device memory (``torch.empty``), streams, autograd bookkeepin
 glue (cat, slicing, SiLU on tiny tensors, masks).
 """
 import ctypes
+import functools
 import os
 import weakref
 from typing import Optional
@@ -23,6 +24,7 @@ _LIB = None
 # signature mini-language: p pointer, l long, i int, f float
 _SIGS = {
     "dfold_abi_version": "",
+    "dfold_capture_id": "pp",
     "dfold_split2d": "plllipl" + "ppll" + "ppll" + "pp",
     "dfold_conv_weight_prep": "piii" + "ppl" + "ppl" + "p",
     "dfold_taps_to_param": "piiipp",
@@ -45,7 +47,7 @@ _SIGS = {
     "dfold_ipa_prob_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
     "dfold_ipa_pair_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
     "dfold_ipa_ds_bwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "ppppp" + "pppp" + "p",
-    "dfold_gemm_bf16x3_batched": "ppllll" + "liill" + "ppllll" + "llil" + "plliлf".replace("л", "l") + "p",
+    "dfold_gemm_bf16x3_batched": "ppllll" + "liill" + "ppllll" + "llil" + "pllilf" + "p",
     "dfold_gemm_wgrad_bf16x3_batched": "pplllll" + "pplllll" + "lll" + "ii" + "iiiil" + "pllf" + "p",
 }
 _CT = {"p": ctypes.c_void_p, "l": ctypes.c_long, "i": ctypes.c_int, "f": ctypes.c_float}
@@ -119,6 +121,26 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_device(fn):
+    """Run an autograd Function's forward / backward with the CUDA device of its tensors current.  The C-ABI launches,
+    cuTensorMapEncode and the stream lookup all act on the CURRENT device, and the reference trainer's single-GPU
+    mode places the model on `cuda:{least loaded}` without torch.cuda.set_device (train_DFOLD_dynamics.py:356,603-606)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise RuntimeError(f"dynamicpdb_b200: operands on different devices ({dev} and {a.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -179,19 +201,36 @@ _WCACHE_EPOCH = 0
 def invalidate_weight_cache():
     """Forget every cached weight plane.  A CUDA-graph replay updates the weights on the device without bumping the
     Python-side version counters, so ``train_step.TrainStep`` calls this after each replay; the next EAGER call then
-    rebuilds its planes from the current weights (replays themselves never consult this cache)."""
+    rebuilds its planes from the current weights (replays themselves never consult this cache).
+    Call it as well after any in-place update made through ``param.data`` (EMA swaps, ``p.data.copy_``, manual clipping):
+    those do not bump ``_version`` either."""
     global _WCACHE_EPOCH
     _WCACHE_EPOCH += 1
+
+
+def _capture_id() -> int:
+    if not torch.cuda.is_current_stream_capturing():
+        return 0
+    out = ctypes.c_ulonglong(0)
+    rc = lib().dfold_capture_id(_stream(), ctypes.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"dfold_capture_id: {lib().dfold_last_error().decode()}")
+    return int(out.value)
 
 
 def _cache_get(kind, w: torch.Tensor, build):
     """bf16 operand planes of a weight, rebuilt whenever the tensor object or its version counter changes
     (optimizer steps and load_state_dict bump ``_version``) or a graph replay may have changed it."""
-    key = (kind, id(w))
+    capturing = _capture_id()
+    key = (kind, id(w), capturing)
     ent = _WCACHE.get(key)
     stamp = (w._version, w.data_ptr(), _WCACHE_EPOCH)
     if ent is not None and ent[0]() is w and ent[1] == stamp:
         return ent[2]
+    # While a CUDA graph is being captured the planes are (re)built INSIDE that capture, from graph-pool memory: a hit on
+    # an eager-pool entry would bake a pointer into the graph that a later eager rebuild frees, and a hit on another
+    # graph's entry would read planes only that other graph refreshes.  Within one capture the same weight is split
+    # once: the entry keyed with this capture's id serves the remaining call sites.
     val = build()
     if len(_WCACHE) > 512:
         for k in [k for k, e in _WCACHE.items() if e[0]() is None]:
@@ -263,6 +302,7 @@ def _use_tensor_cores(M: int, N: int, K: int) -> bool:
 # --------------------------------------------------------------------------------------------------
 class _LinearFn(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, w, b, act, residual, pre_relu):
         _need_cuda(x, w, b, residual)
         K_ = w.shape[1]
@@ -289,6 +329,7 @@ class _LinearFn(Function):
         return out.reshape(x.shape[:-1] + (N_,))
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         x2, w, out, r2, a_hi, a_lo = ctx.saved_tensors
         xshape, act, pre_relu, tc, has_b, rshape = ctx.meta
@@ -349,6 +390,7 @@ def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, pre_r
 # --------------------------------------------------------------------------------------------------
 class _Conv5x5Fn(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, w, b, relu, residual, crop):
         _need_cuda(x, w, b, residual)
         F_, N_, Ci = x.shape
@@ -370,6 +412,7 @@ class _Conv5x5Fn(Function):
         return out.reshape(Fo, N_, Co)
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         x_hi, x_lo, w, out, r2 = ctx.saved_tensors
         (F_, N_, Ci), relu, has_b, has_r, crop = ctx.meta
@@ -410,6 +453,7 @@ def conv5x5(x, weight, bias=None, relu: bool = True, residual=None, crop: int = 
 # --------------------------------------------------------------------------------------------------
 class _GlobalLNFn(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, eps, silu):
         _need_cuda(x)
         xc = _f32c(x)
@@ -423,6 +467,7 @@ class _GlobalLNFn(Function):
         return y
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         xc, stats = ctx.saved_tensors
         g = _f32c(dy)
@@ -440,6 +485,7 @@ def global_layernorm(x, eps: float = 1e-4, silu: bool = False):
 
 class _RowLNFn(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, x, w, b, eps):
         _need_cuda(x, w, b)
         C = x.shape[-1]
@@ -454,6 +500,7 @@ class _RowLNFn(Function):
         return y.reshape(x.shape)
 
     @staticmethod
+    @_on_device
     def backward(ctx, dy):
         x2, w, stats = ctx.saved_tensors
         C = x2.shape[1]
@@ -476,6 +523,7 @@ def layer_norm(x, weight, bias, eps: float = 1e-5):
 # --------------------------------------------------------------------------------------------------
 class _QuatToRotFn(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, q):
         _need_cuda(q)
         qc = _f32c(q)
@@ -486,6 +534,7 @@ class _QuatToRotFn(Function):
         return R
 
     @staticmethod
+    @_on_device
     def backward(ctx, dR):
         (qc,) = ctx.saved_tensors
         dq = torch.empty_like(qc)
@@ -504,6 +553,7 @@ class _RigidApplyFn(Function):
     """quat [F,N,4], trans [F,N,3], pts [Fp,N,m,3] with Fp in {1, F} -> [F,N,m,3]."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, quat, trans, pts, inverse):
         F_, N_ = quat.shape[0], quat.shape[1]
         m = pts.shape[2]
@@ -516,6 +566,7 @@ class _RigidApplyFn(Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dout):
         quat, trans, pts = ctx.saved_tensors
         F_, N_ = quat.shape[0], quat.shape[1]
@@ -574,6 +625,7 @@ def ipa_points(raw, quat, trans, H: int):
 
 class _ComposeFn(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, quat, trans, upd, mask):
         _need_cuda(quat, trans, upd, mask)
         qc, tc, uc = _f32c(quat), _f32c(trans), _f32c(upd)
@@ -586,6 +638,7 @@ class _ComposeFn(Function):
         return qo, to
 
     @staticmethod
+    @_on_device
     def backward(ctx, dqo, dto):
         qc, uc, mc = ctx.saved_tensors
         n = qc.numel() // 4
@@ -613,6 +666,7 @@ class _QKLogitsFn(Function):
     """logit0[f,h,i,j] = alpha * q[f,i,h,:] . k[f,j,h,:] + beta * b[f,h,i,j]   (k = first C of each kv head)."""
 
     @staticmethod
+    @_on_device
     def forward(ctx, q, kv, b_hm, alpha, beta):
         _need_cuda(q, kv, b_hm)
         Fs, N_, H_, C_ = q.shape
@@ -632,6 +686,7 @@ class _QKLogitsFn(Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, dl):
         q, kv = ctx.saved_tensors
         alpha, beta, Fz, bshape = ctx.meta
@@ -662,6 +717,7 @@ def qk_logits(q, kv, b_hm, alpha: float, beta: float):
 
 class _IpaAttnFn(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps):
         _need_cuda(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma)
         logit0, kv, q_pts, kv_pts, pair = _f32c(logit0), _f32c(kv), _f32c(q_pts), _f32c(kv_pts), _f32c(pair)
@@ -691,6 +747,7 @@ class _IpaAttnFn(Function):
                 _ptr(mask), _ptr(gamma), F_, N_, H_, C_, Pq, Pv, Cp, int(dfold), inf, eps)
 
     @staticmethod
+    @_on_device
     def backward(ctx, dcat):
         logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, cat, lse = ctx.saved_tensors
         Pq, Pv, dfold, inf, eps = ctx.meta
@@ -763,6 +820,7 @@ class _IpaAttnTCFn(Function):
                 _ptr(gamma), _ptr(p_hi), _ptr(p_lo), ldp, F_, N_, H_, C_, Pq, Pv, Cp, int(dfold), inf, eps)
 
     @staticmethod
+    @_on_device
     def forward(ctx, logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps):
         _need_cuda(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma)
         logit0, kv, q_pts, kv_pts, pair = _f32c(logit0), _f32c(kv), _f32c(q_pts), _f32c(kv_pts), _f32c(pair)
@@ -793,6 +851,7 @@ class _IpaAttnTCFn(Function):
         return cat
 
     @staticmethod
+    @_on_device
     def backward(ctx, dcat):
         logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, cat, p_hi, p_lo = ctx.saved_tensors
         Pq, Pv, dfold, inf, eps = ctx.meta
@@ -866,12 +925,14 @@ class _IpaAttnTCFn(Function):
         return dlogit0, dkv, dq_pts, dkv_pts, dpair, dquat, dtrans, None, dgamma, None, None, None, None, None
 
 
-def _tc_path_ok(logit0, kv, q_pts, pair) -> bool:
+def _tc_path_ok(logit0, kv, q_pts, pair, Pq, Pv) -> bool:
     """The tensor-core decomposition needs frame-shared q/k/v and pair tensors, a head width that is a whole number
-    of 64-wide K blocks, and rows that fit in shared memory."""
+    of 64-wide K blocks, rows that fit in shared memory and point counts within its register tiles
+    (csrc/ipa_v2.cu v2_params: 3*Pq <= 48, 3*Pv <= 64)."""
     C_ = kv.shape[-1] // 2
     N_ = q_pts.shape[1]
-    return kv.shape[0] == 1 and pair.shape[0] == 1 and C_ % 64 == 0 and N_ <= 1280 and N_ % 8 == 0 and pair.shape[-1] % 8 == 0
+    return (kv.shape[0] == 1 and pair.shape[0] == 1 and C_ % 64 == 0 and N_ <= 1280 and N_ % 8 == 0
+            and pair.shape[-1] % 8 == 0 and 3 * Pq <= 48 and 3 * Pv <= 64)
 
 
 def ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, *, Pq, Pv, dfold, inf, eps):
@@ -879,6 +940,6 @@ def ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, *, 
 
     Frame-shared q/k/v with C % 64 == 0 (DFOLDv2, preset A) runs the tensor-core decomposition (csrc/ipa_v2.cu);
     every other shape runs the single fused CUDA-core kernel (csrc/ipa_attn.cu).  Both are this library's kernels."""
-    if _tc_path_ok(logit0, kv, q_pts, pair):
+    if _tc_path_ok(logit0, kv, q_pts, pair, Pq, Pv):
         return _IpaAttnTCFn.apply(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps)
     return _IpaAttnFn.apply(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps)

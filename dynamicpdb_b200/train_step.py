@@ -14,6 +14,10 @@ time as device time, so the B200-native step is:
   by-value kernel arguments), replays have no Python / launch overhead;
 * if capture is not possible the same step runs eagerly (``graph=False`` or on capture failure).
 """
+import copy
+import os
+import sys
+import time
 from typing import Callable, Dict, Optional
 
 import torch
@@ -41,8 +45,13 @@ class TrainStep:
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_error: Optional[str] = None
-        import os, sys, time
         verbose = os.environ.get("DFOLD_BENCH_VERBOSE", "0") == "1"
+        # The warm-up steps below are REAL steps (they must be: they size the allocator pools and initialise NCCL and the
+        # capturable Adam state before capture).  Training must nevertheless start from the weights and optimizer state
+        # the caller handed in, so both are snapshotted here and restored after capture.
+        with torch.no_grad():
+            saved_params = [p.detach().clone() for p in self.params]
+        saved_opt = copy.deepcopy(self.opt.state_dict())
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -55,6 +64,7 @@ class TrainStep:
         torch.cuda.synchronize()
         if graph:
             try:
+                _kernels.invalidate_weight_cache()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._eager()
@@ -63,6 +73,29 @@ class TrainStep:
                 self.graph_error = f"{type(e).__name__}: {str(e)[:200]}"
                 self.graph = None
                 torch.cuda.synchronize()
+        self._restore(saved_params, saved_opt)
+
+    def _restore(self, saved_params, saved_opt):
+        """Undo the warm-up / capture steps: parameters back to their values at construction; Adam moments zeroed and the
+        step counter reset IN PLACE (the captured graph holds pointers to these very state tensors)."""
+        with torch.no_grad():
+            for p, v in zip(self.params, saved_params):
+                p.copy_(v)
+            fresh = not saved_opt["state"]
+            for i, p in enumerate(self.params):
+                st = self.opt.state.get(p)
+                if not st:
+                    continue
+                old = None if fresh else saved_opt["state"].get(i)
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        if old is not None and k in old:
+                            v.copy_(old[k].to(v.device))
+                        else:
+                            v.zero_()
+            self.flat_grad.zero_()
+        _kernels.invalidate_weight_cache()
+        torch.cuda.synchronize()
 
     def _eager(self):
         self.flat_grad.zero_()

@@ -21,6 +21,9 @@ extern "C" {
 
 const char* dfold_last_error(void);
 int dfold_abi_version(void);
+/* Host-side helper: *id_out = id of the CUDA-graph capture `stream` is recording into, 0 when not capturing
+ * (HOST pointer). */
+int dfold_capture_id(void* stream, unsigned long long* id_out);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Split-precision tensor-core GEMM (tcgen05, bf16 x 3, fp32 accumulate in TMEM) and its operand preparation.

@@ -65,6 +65,26 @@ def run_net(name, c):
     print(name, "loss", float(loss), "params", len(sd))
 
 
+def run_net_big(name="net_A256", nf=64, N=256, seed=7):
+    """The BENCHED shape (BASELINE.json configs[2]: preset A, 64 frames x 256 residues), forward only under no_grad
+    (the unmodified reference materialises [nf,N,N,H,Pq,3] tensors; ~25 GB peak).  Stores every small output whole and
+    the last two frames of the atom tensors."""
+    c = dict(preset="PRESET_A", nf=nf, N=N, seed=seed)
+    conf = syn.model_conf(nf, **syn.PRESET_A)
+    net = RefNet.FullScoreNetwork(conf, se3_diffuser.SE3Diffuser(syn.diffuser_conf(1.0)))
+    sd = syn.random_state({k: v.shape for k, v in net.state_dict().items()}, seed=seed + 100)
+    net.load_state_dict(sd)
+    with torch.no_grad():
+        out = net(case_feats(c))
+    keep = {}
+    for k, v in out.items():
+        v = v.detach()
+        keep[k] = v[-2:].clone() if k in ("atom37", "atom14") else v.clone()
+    torch.save({"case": c, "shapes": {k: tuple(v.shape) for k, v in sd.items()}, "out": keep,
+                "loss": float(syn.surrogate_loss(out))}, os.path.join(OUT, name + ".pt"))
+    print(name, "loss", float(syn.surrogate_loss(out)))
+
+
 def run_vanilla():
     torch.manual_seed(0)
     c_s, c_z, c_h, H, Pq, Pv, N, B = 32, 16, 8, 4, 4, 8, 14, 2
@@ -151,6 +171,9 @@ def run_transitions():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        run_net_big()
+        sys.exit(0)
     run_transitions()
     for n, c in NET_CASES.items():
         run_net(n, c)

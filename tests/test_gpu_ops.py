@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _run(fn, inputs, kwargs, dtype, device):
+def _run(fn, inputs, kwargs, dtype, device, wmask=None):
     xs = []
     for t in inputs:
         if isinstance(t, torch.Tensor) and t.is_floating_point():
@@ -39,39 +39,46 @@ def _run(fn, inputs, kwargs, dtype, device):
     g = torch.Generator().manual_seed(7)
     loss = 0
     for o in outs:
-        w = torch.randn(o.shape, generator=g).to(device=device, dtype=o.dtype)
+        w = torch.randn(o.shape, generator=g)
+        if wmask is not None:
+            w = w * wmask.reshape(o.shape)
+        w = w.to(device=device, dtype=o.dtype)
         loss = loss + (o * w).sum()
     leaves = [x for x in xs if isinstance(x, torch.Tensor) and x.requires_grad]
     grads = torch.autograd.grad(loss, leaves, allow_unused=True) if leaves else []
     return [o.detach().double().cpu() for o in outs], [None if gr is None else gr.detach().double().cpu() for gr in grads]
 
 
-def _rel_err(a, b, outliers):
-    """max |a-b| / max|a|, ignoring the `outliers` largest deviations (ReLU gates that flip between the fp64
-    reference and the fp32 kernel when a pre-activation is within rounding of zero)."""
-    d = (a - b).abs().flatten()
-    if outliers:
-        k = min(d.numel() - 1, int(outliers))
-        d = torch.topk(d, k + 1).values[-1:]
-    return d.max().item() / (a.abs().max().item() + 1e-30)
+def _rel_err(a, b):
+    """max |a-b| / max|a| over EVERY element (no outlier allowance)."""
+    return (a - b).abs().max().item() / (a.abs().max().item() + 1e-30)
 
 
-def check(name, inputs, tol, post=None, outliers=0, **kwargs):
+def _safe_gate(pre, tau=1e-3):
+    """Output positions whose ReLU pre-activation (fp64 oracle) is further than tau * max|pre| from zero.  The
+    upstream gradient of BOTH sides is zeroed elsewhere, so oracle and kernel see the same ReLU gate by construction:
+    a pre-activation within rounding of zero may gate differently in fp64 and in the kernel, and that is a property
+    of the comparison, not of the kernel.  Every element of every gradient is then compared, none is discarded."""
+    pre = pre.detach().double()
+    return (pre.abs() > tau * pre.abs().max()).to(torch.float64)
+
+
+def check(name, inputs, tol, post=None, wmask=None, **kwargs):
     fo = getattr(O, name) if post is None else (lambda *a, **k: post(getattr(O, name)(*a, **k), *a))
     fk = getattr(K, name) if post is None else (lambda *a, **k: post(getattr(K, name)(*a, **k), *a))
-    ro, rg = _run(fo, inputs, kwargs, torch.float64, "cpu")
-    co, cg = _run(fk, inputs, kwargs, torch.float32, DEV)
+    ro, rg = _run(fo, inputs, kwargs, torch.float64, "cpu", wmask)
+    co, cg = _run(fk, inputs, kwargs, torch.float32, DEV, wmask)
     torch.cuda.synchronize()
     for i, (a, b) in enumerate(zip(ro, co)):
         assert a.shape == b.shape, f"{name} out{i} shape {a.shape} vs {b.shape}"
-        err = _rel_err(a, b, 0)
+        err = _rel_err(a, b)
         assert err < tol, f"{name} out{i}: rel err {err:.3e} >= {tol}"
     for i, (a, b) in enumerate(zip(rg, cg)):
         assert (a is None) == (b is None), f"{name} grad{i} presence"
         if a is None:
             continue
         assert a.shape == b.shape, f"{name} grad{i} shape {a.shape} vs {b.shape}"
-        err = _rel_err(a, b, outliers)
+        err = _rel_err(a, b)
         assert err < tol, f"{name} grad{i}: rel err {err:.3e} >= {tol}"
 
 
@@ -86,7 +93,7 @@ def unit(*s, grad=True):
 
 
 def test_library_loads():
-    assert K.lib().dfold_abi_version() == 1
+    assert K.lib().dfold_abi_version() == 2
 
 
 @pytest.mark.parametrize("M,Kd,N", [(5, 3, 16), (70, 14, 32), (33, 7, 6), (256, 160, 6), (100, 128, 8), (4096, 7, 6), (3000, 14, 32)])
@@ -100,10 +107,11 @@ def test_linear_simt(M, Kd, N, act, pre_relu, res):
 @pytest.mark.parametrize("act,pre_relu,res", [(None, False, False), ("relu", False, True), (None, True, True)])
 def test_linear_tensor_core(M, Kd, N, act, pre_relu, res):
     inputs = [R(M, Kd), R(N, Kd, scale=1.0 / math.sqrt(Kd)), R(N)]
-    # a ReLU whose pre-activation is within fp32 rounding of 0 may gate differently than the fp64 reference: allow
-    # that many isolated rows/columns of the gradients to deviate
-    check("linear", inputs, 1e-4, outliers=(6 * max(M, Kd, N) if (act or pre_relu) else 0), act=act, pre_relu=pre_relu,
-          residual=R(M, N) if res else None)
+    wmask = None
+    if act == "relu":
+        with torch.no_grad():
+            wmask = _safe_gate(O.linear(*[t.double() for t in inputs], act=None, pre_relu=pre_relu))
+    check("linear", inputs, 1e-4, wmask=wmask, act=act, pre_relu=pre_relu, residual=R(M, N) if res else None)
 
 
 @pytest.mark.parametrize("F,N,Ci,Co", [(2, 16, 160, 80), (3, 12, 80, 160), (5, 130, 64, 128), (8, 256, 320, 256), (1, 40, 256, 640)])
@@ -111,7 +119,11 @@ def test_linear_tensor_core(M, Kd, N, act, pre_relu, res):
 def test_conv5x5(F, N, Ci, Co, relu, res):
     inputs = [R(F, N, Ci), R(Co, Ci, 5, 5, scale=1.0 / math.sqrt(25 * Ci)), R(Co)]
     residual = R(F, N, Co) if res else None
-    check("conv5x5", inputs, 1e-4, outliers=(60 * max(Ci, Co) if relu else 0), relu=relu, residual=residual)
+    wmask = None
+    if relu:
+        with torch.no_grad():
+            wmask = _safe_gate(O.conv5x5(*[t.double() for t in inputs], relu=False))
+    check("conv5x5", inputs, 1e-4, wmask=wmask, relu=relu, residual=residual)
 
 
 @pytest.mark.parametrize("shape", [(3, 12, 32), (8, 256, 256), (1, 7, 5)])
@@ -188,4 +200,8 @@ def test_conv5x5_cropped(F, N, Ci, Co, crop, relu, res):
     """Only the last F - crop output frames (dead-frame pyramid): forward, data gradient and weight gradient."""
     inputs = [R(F, N, Ci), R(Co, Ci, 5, 5, scale=1.0 / math.sqrt(25 * Ci)), R(Co)]
     residual = R(F - crop, N, Co) if res else None
-    check("conv5x5", inputs, 1e-4, outliers=(60 * max(Ci, Co) if relu else 0), relu=relu, residual=residual, crop=crop)
+    wmask = None
+    if relu:
+        with torch.no_grad():
+            wmask = _safe_gate(O.conv5x5(*[t.double() for t in inputs], relu=False, crop=crop))
+    check("conv5x5", inputs, 1e-4, wmask=wmask, relu=relu, residual=residual, crop=crop)
