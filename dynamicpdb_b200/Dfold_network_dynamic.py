@@ -114,11 +114,8 @@ class FullScoreNetwork(nn.Module):
         }
         rigids_pred = model_out["final_rigids"]
         pred_out["rigids"] = rigids_pred.to_tensor_7()
-        all_frames = feats.torsion_angles_to_frames(
-            rigids_pred, angles_pred, input_feats["aatype"],
-            feats.table("default_frames", angles_pred.device))
-        atom14_pos = feats.frames_to_atom14_pos(all_frames, input_feats["aatype"])
-        atom37_pos, _ = atom14_to_atom37(atom14_pos, input_feats["aatype"])
+        # torsion frames -> atom14 -> atom37 (ref :532-538) in one kernel
+        atom14_pos, atom37_pos = feats.frames_to_atoms(rigids_pred, angles_pred, input_feats["aatype"])
         pred_out["atom37"] = atom37_pos
         pred_out["atom14"] = atom14_pos
         pred_out["rigid_update"] = model_out["rigid_update"]

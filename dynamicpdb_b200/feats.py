@@ -12,6 +12,7 @@ from typing import Dict, Tuple
 import numpy as np
 import torch
 
+from . import kernels as K
 from .rigid_utils import Rigid, Rotation
 
 _NPZ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "residue_tables.npz")
@@ -80,3 +81,28 @@ def atom14_to_atom37(atom14_data: torch.Tensor, aatype: torch.Tensor):
         out = torch.gather(atom14_data, -2, idx[..., None].expand(idx.shape + (atom14_data.shape[-1],)))
         return out * mask[..., None].to(out.dtype), mask
     raise ValueError("Incorrectly shaped data")
+
+
+_TABLE_NAMES = ("default_frames", "atom14_group", "atom14_mask", "atom14_pos", "atom37_to_atom14", "atom37_mask")
+
+
+def _eager_chain(rot_is_matrix: bool):
+    """The differentiable statement of the fused kernel (used by its backward): the three reference-shaped functions above."""
+    def run(rot, trans, alpha, aatype, want_frames):
+        rots = Rotation(rot_mats=rot) if rot_is_matrix else Rotation(quats=rot, normalize_quats=False)
+        frames = torsion_angles_to_frames(Rigid(rots, trans), alpha, aatype, table("default_frames", alpha.device, alpha.dtype))
+        a14 = frames_to_atom14_pos(frames, aatype)
+        a37, _ = atom14_to_atom37(a14, aatype)
+        return (a14, a37, frames.to_tensor_4x4()) if want_frames else (a14, a37)
+    return run
+
+
+def frames_to_atoms(r: Rigid, alpha: torch.Tensor, aatype: torch.Tensor, want_frames: bool = False):
+    """``torsion_angles_to_frames`` -> ``frames_to_atom14_pos`` -> ``atom14_to_atom37`` as ONE kernel (csrc/epilogue.cu
+    `frames_to_atoms_kernel`, K10): r Rigid[*,N], alpha [*,N,7,2], aatype [*,N] -> (atom14 [*,N,14,3], atom37 [*,N,37,3]
+    [, frames [*,N,8,4,4]]).  fp32 out whatever alpha's dtype, as the reference (Rotation forces fp32)."""
+    rots = r.get_rots()
+    is_mat = rots._quats is None
+    rot = rots.get_rot_mats() if is_mat else rots.get_quats()
+    tables = {k: table(k, alpha.device) for k in _TABLE_NAMES}
+    return K.frames_to_atoms(rot, r.get_trans(), alpha, aatype, tables, _eager_chain(is_mat), want_frames, is_mat)

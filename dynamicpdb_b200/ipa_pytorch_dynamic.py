@@ -290,6 +290,9 @@ class DFOLDIpaScore(nn.Module):
         ipa_conf = model_conf.ipa
         self._ipa_conf = ipa_conf
         self.diffuser = diffuser
+        # device-resident twin of the caller's diffuser for the fused score epilogue (None: use the object as handed in)
+        from .score_epilogue import SE3ScoreDiffuser
+        self._fused_scores = diffuser if isinstance(diffuser, SE3ScoreDiffuser) else SE3ScoreDiffuser.from_reference(diffuser)
 
         self.scale_pos = lambda x: x * ipa_conf.coordinate_scaling
         self.scale_rigids = lambda x: x.apply_trans_fn(self.scale_pos)
@@ -365,12 +368,18 @@ class DFOLDIpaScore(nn.Module):
 
         unorm_angles, angles = self.angle_resnet(node_feat, init_node_feat)
         curr_rigids = Rigid.from_tensor_7(curr)
-        rot_score = self.diffuser.calc_rot_score(init_rigids.get_rots(), curr_rigids.get_rots(), t)
-        rot_score = rot_score * node_mask[..., None]
-        curr_rigids = self.unscale_rigids(curr_rigids)
-        trans_score = self.diffuser.calc_trans_score(init_rigids.get_trans(), curr_rigids.get_trans(),
-                                                     t[:, None, None], use_torch=True)
-        trans_score = trans_score * node_mask[..., None]
+        if self._fused_scores is not None:
+            # ref :883-897 in one kernel: rotation score (IGSO(3) series, fp64), unscale, translation score, masks
+            rot_score, trans_score = self._fused_scores.fused_scores(init_rigids, curr_rigids, t, node_mask,
+                                                                     self._ipa_conf.coordinate_scaling)
+            curr_rigids = self.unscale_rigids(curr_rigids)
+        else:
+            rot_score = self.diffuser.calc_rot_score(init_rigids.get_rots(), curr_rigids.get_rots(), t)
+            rot_score = rot_score * node_mask[..., None]
+            curr_rigids = self.unscale_rigids(curr_rigids)
+            trans_score = self.diffuser.calc_trans_score(init_rigids.get_trans(), curr_rigids.get_trans(),
+                                                         t[:, None, None], use_torch=True)
+            trans_score = trans_score * node_mask[..., None]
         return {
             "angles": angles,
             "unorm_angles": unorm_angles,

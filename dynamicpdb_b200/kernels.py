@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfold_b200.so")
 _LIB = None
 
-# signature mini-language: p pointer, l long, i int, f float
+# signature mini-language: p pointer, l long, i int, f float, d double
 _SIGS = {
     "dfold_abi_version": "",
     "dfold_capture_id": "pp",
@@ -49,8 +49,15 @@ _SIGS = {
     "dfold_ipa_ds_bwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "ppppp" + "pppp" + "p",
     "dfold_gemm_bf16x3_batched": "ppllll" + "liill" + "ppllll" + "llil" + "pllilf" + "p",
     "dfold_gemm_wgrad_bf16x3_batched": "pplllll" + "pplllll" + "lll" + "ii" + "iiiil" + "pllf" + "p",
+    "dfold_score_fwd": "ppppp" + "pidddd" + "ffpil" + "ppi" + "p",
+    "dfold_score_bwd": "ppppp" + "pidddd" + "ffpil" + "ppi" + "pp" + "p",
+    "dfold_frames_to_atoms_fwd": "pippp" + "pppppp" + "ppp" + "lp",
+    "dfold_quat_mul_fwd": "ppplip",
+    "dfold_quat_mul_bwd": "ppppplip",
+    "dfold_rot_compose_fwd": "pppp" + "pp" + "liip",
+    "dfold_rot_compose_bwd": "pppp" + "pp" + "pppp" + "liip",
 }
-_CT = {"p": ctypes.c_void_p, "l": ctypes.c_long, "i": ctypes.c_int, "f": ctypes.c_float}
+_CT = {"p": ctypes.c_void_p, "l": ctypes.c_long, "i": ctypes.c_int, "f": ctypes.c_float, "d": ctypes.c_double}
 
 
 def lib():
@@ -943,3 +950,215 @@ def ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, *, 
     if _tc_path_ok(logit0, kv, q_pts, pair, Pq, Pv):
         return _IpaAttnTCFn.apply(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps)
     return _IpaAttnFn.apply(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq, Pv, dfold, inf, eps)
+
+
+# --------------------------------------------------------------------------------------------------
+# score epilogue (K9), structure epilogue (K10), remaining rigid algebra — csrc/epilogue.cu
+# --------------------------------------------------------------------------------------------------
+class _ScoreFn(Function):
+    """(q_pred, q_t, x_pred, x_t) -> (rot_score fp64 [...,3], trans_score [...,3]); see include/dfold_b200.h."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, q_pred, q_t, x_pred, x_t, t64, grid, mask, consts, trans_f64):
+        _need_cuda(q_pred, q_t, x_pred, x_t, t64, grid, mask)
+        q_pred, q_t = _f32c(q_pred), _f32c(q_t)
+        x_pred, x_t = (_f32c(x_pred), _f32c(x_t)) if x_pred is not None else (None, None)
+        mask = _f32c(mask) if mask is not None else None
+        n = q_pred.numel() // 4
+        rot = torch.empty(q_pred.shape[:-1] + (3,), dtype=torch.float64, device=q_pred.device)
+        trs = None
+        if x_pred is not None:
+            trs = torch.empty(x_pred.shape[:-1] + (3,), dtype=torch.float64 if trans_f64 else torch.float32, device=q_pred.device)
+        max_s, min_s, min_b, max_b, r3, ipa, L = consts
+        _check(lib().dfold_score_fwd(_ptr(q_pred), _ptr(q_t), _ptr(x_pred), _ptr(x_t), _ptr(t64), _ptr(grid), grid.numel(),
+                                     max_s, min_s, min_b, max_b, r3, ipa, _ptr(mask), L, n, _ptr(rot), _ptr(trs), int(trans_f64),
+                                     _stream()), "dfold_score_fwd")
+        ctx.save_for_backward(q_pred, q_t, x_pred, x_t, t64, grid, mask)
+        ctx.meta = (consts, trans_f64)
+        return rot, trs
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, d_rot, d_trs):
+        q_pred, q_t, x_pred, x_t, t64, grid, mask = ctx.saved_tensors
+        consts, trans_f64 = ctx.meta
+        max_s, min_s, min_b, max_b, r3, ipa, L = consts
+        n = q_pred.numel() // 4
+        d_rot = d_rot.to(torch.float64).contiguous() if d_rot is not None else None
+        d_trs = d_trs.to(torch.float64 if trans_f64 else torch.float32).contiguous() if d_trs is not None else None
+        dq = torch.empty_like(q_pred)
+        dx = torch.empty_like(x_pred) if x_pred is not None else None
+        _check(lib().dfold_score_bwd(_ptr(q_pred), _ptr(q_t), _ptr(x_pred), _ptr(x_t), _ptr(t64), _ptr(grid), grid.numel(),
+                                     max_s, min_s, min_b, max_b, r3, ipa, _ptr(mask), L, n, _ptr(d_rot), _ptr(d_trs), int(trans_f64),
+                                     _ptr(dq), _ptr(dx), _stream()), "dfold_score_bwd")
+        return dq, None, dx, None, None, None, None, None, None
+
+
+def score_epilogue(q_pred, q_t, x_pred, x_t, t, grid, mask, *, max_sigma, min_sigma, min_b, max_b, r3_scale, ipa_scale, L=1000):
+    """IGSO(3) rotation score (fp64) and VP-SDE translation score of the predicted frames against the noised ones at
+    diffusion time ``t`` ([1] tensor), both multiplied by ``mask`` [...]; the translation score takes the dtype
+    ``promote(float32, t.dtype)`` as the reference arithmetic does.  ``x_pred`` is the translation BEFORE unscaling."""
+    t64 = t.reshape(-1)[:1].to(torch.float64)
+    trans_f64 = t.dtype == torch.float64
+    consts = (float(max_sigma), float(min_sigma), float(min_b), float(max_b), float(r3_scale), float(ipa_scale), int(L))
+    return _ScoreFn.apply(q_pred, q_t, x_pred, x_t, t64, grid, mask, consts, trans_f64)
+
+
+class _FramesToAtomsFn(Function):
+    """Forward: ONE kernel.  Backward (atoms are not in the reference's training loss, train_DFOLD_dynamics.py:1367-1373,
+    but stay differentiable): recomputation through ``eager`` — the same chain written with the differentiable rigid
+    operators of this module — under enable_grad."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, rot, trans, alpha, aatype, tables, eager, want_frames, rot_is_matrix):
+        _need_cuda(rot, trans, alpha, aatype)
+        rotc, transc, alphac = _f32c(rot), _f32c(trans), _f32c(alpha)
+        aac = aatype.to(torch.int64).contiguous()
+        lead = aac.shape
+        n = aac.numel()
+        dev = rotc.device
+        a14 = torch.empty(lead + (14, 3), dtype=torch.float32, device=dev)
+        a37 = torch.empty(lead + (37, 3), dtype=torch.float32, device=dev)
+        fr = torch.empty(lead + (8, 4, 4), dtype=torch.float32, device=dev) if want_frames else None
+        _check(lib().dfold_frames_to_atoms_fwd(_ptr(rotc), int(rot_is_matrix), _ptr(transc), _ptr(alphac), _ptr(aac),
+                                               *[_ptr(tables[k]) for k in ("default_frames", "atom14_group", "atom14_mask",
+                                                                           "atom14_pos", "atom37_to_atom14", "atom37_mask")],
+                                               _ptr(fr), _ptr(a14), _ptr(a37), n, _stream()), "dfold_frames_to_atoms_fwd")
+        ctx.save_for_backward(rotc, transc, alphac, aac)
+        ctx.eager = eager
+        ctx.want_frames = want_frames
+        if want_frames:
+            return a14, a37, fr
+        return a14, a37
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, *gouts):
+        rotc, transc, alphac, aac = ctx.saved_tensors
+        with torch.enable_grad():
+            ins = [t.detach().requires_grad_(True) for t in (rotc, transc, alphac)]
+            outs = ctx.eager(ins[0], ins[1], ins[2], aac, ctx.want_frames)
+            pairs = [(o, g) for o, g in zip(outs, gouts) if g is not None]
+            grads = torch.autograd.grad([o for o, _ in pairs], ins, [g for _, g in pairs], allow_unused=True)
+        return grads[0], grads[1], grads[2], None, None, None, None, None
+
+
+def frames_to_atoms(rot, trans, alpha, aatype, tables, eager, want_frames=False, rot_is_matrix=False):
+    """(backbone rotation [*,N,4] quaternion or [*,N,3,3], translation [*,N,3], torsions [*,N,7,2], aatype [*,N]) ->
+    (atom14 [*,N,14,3], atom37 [*,N,37,3][, frames [*,N,8,4,4]])."""
+    return _FramesToAtomsFn.apply(rot, trans, alpha, aatype, tables, eager, want_frames, rot_is_matrix)
+
+
+class _QuatMulFn(Function):
+    @staticmethod
+    @_on_device
+    def forward(ctx, a, b, b_is_vec):
+        _need_cuda(a, b)
+        shp = torch.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+        ac = _f32c(a.expand(shp + (4,)))
+        bc = _f32c(b.expand(shp + (b.shape[-1],)))
+        out = torch.empty(shp + (4,), dtype=torch.float32, device=a.device)
+        n = out.numel() // 4
+        if n:
+            _check(lib().dfold_quat_mul_fwd(_ptr(ac), _ptr(bc), _ptr(out), n, int(b_is_vec), _stream()), "dfold_quat_mul_fwd")
+        ctx.save_for_backward(ac, bc)
+        ctx.meta = (a.shape, b.shape, b_is_vec)
+        return out
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, g):
+        ac, bc = ctx.saved_tensors
+        ashape, bshape, b_is_vec = ctx.meta
+        g = _f32c(g)
+        da, db = torch.empty_like(ac), torch.empty_like(bc)
+        n = ac.numel() // 4
+        if n:
+            _check(lib().dfold_quat_mul_bwd(_ptr(ac), _ptr(bc), _ptr(g), _ptr(da), _ptr(db), n, int(b_is_vec), _stream()), "dfold_quat_mul_bwd")
+        return da.sum_to_size(ashape) if da.shape != ashape else da, db.sum_to_size(bshape) if db.shape != bshape else db, None
+
+
+def quat_mul(a, b, b_is_vec: bool = False):
+    """Hamilton product a (x) b; ``b_is_vec``: b [...,3] is the pure quaternion (0, b)."""
+    return _QuatMulFn.apply(a, b, b_is_vec)
+
+
+def _trailing_rep(a_lead, b_lead):
+    """b_lead = a_lead[:k] + extra with a_lead[k:] all ones (the ``r[..., None].compose(x)`` idiom) -> numel(extra)."""
+    if len(a_lead) != len(b_lead):
+        return None
+    k = len(a_lead)
+    while k > 0 and a_lead[k - 1] == 1:
+        k -= 1
+    if tuple(a_lead[:k]) != tuple(b_lead[:k]):
+        return None
+    rep = 1
+    for d in b_lead[k:]:
+        rep *= d
+    return rep
+
+
+class _RotComposeFn(Function):
+    """(Ra [A,3,3], ta [A,3]|None) o (Rb [B,3,3]|None, tb [B,3]|None); A broadcasts over trailing dims of B."""
+
+    @staticmethod
+    @_on_device
+    def forward(ctx, Ra, ta, Rb, tb, inverse):
+        _need_cuda(Ra, ta, Rb, tb)
+        a_lead = tuple(Ra.shape[:-2])
+        b_lead = tuple(Rb.shape[:-2]) if Rb is not None else tuple(tb.shape[:-1])
+        if Rb is not None and tb is not None and tuple(tb.shape[:-1]) != b_lead:
+            lead = torch.broadcast_shapes(b_lead, tb.shape[:-1])
+            Rb, tb, b_lead = Rb.expand(lead + (3, 3)), tb.expand(lead + (3,)), tuple(lead)
+        out_lead = tuple(torch.broadcast_shapes(a_lead, b_lead))
+        rep = _trailing_rep(a_lead, out_lead) if len(a_lead) == len(out_lead) else None
+        if rep is None or b_lead != out_lead:
+            # general broadcast: materialise both sides at the output shape
+            Ra_e, ta_e = Ra.expand(out_lead + (3, 3)), (ta.expand(out_lead + (3,)) if ta is not None else None)
+            Rb = Rb.expand(out_lead + (3, 3)) if Rb is not None else None
+            tb = tb.expand(out_lead + (3,)) if tb is not None else None
+            rep = 1
+        else:
+            Ra_e, ta_e = Ra, (ta.expand(a_lead + (3,)) if ta is not None else None)
+        Rac, tac = _f32c(Ra_e), (_f32c(ta_e) if ta_e is not None else None)
+        Rbc, tbc = (_f32c(Rb) if Rb is not None else None), (_f32c(tb) if tb is not None else None)
+        na = Rac.numel() // 9
+        dev = Rac.device
+        Ro = torch.empty(out_lead + (3, 3), dtype=torch.float32, device=dev) if Rbc is not None else None
+        to = torch.empty(out_lead + (3,), dtype=torch.float32, device=dev) if tbc is not None else None
+        if na:
+            _check(lib().dfold_rot_compose_fwd(_ptr(Rac), _ptr(tac), _ptr(Rbc), _ptr(tbc), _ptr(Ro), _ptr(to), na, rep, int(inverse),
+                                               _stream()), "dfold_rot_compose_fwd")
+        ctx.save_for_backward(Rac, tac, Rbc, tbc)
+        ctx.meta = (tuple(Ra.shape), tuple(ta.shape) if ta is not None else None, tuple(Rb.shape) if Rb is not None else None,
+                    tuple(tb.shape) if tb is not None else None, rep, inverse, na)
+        return Ro, to
+
+    @staticmethod
+    @_on_device
+    def backward(ctx, dRo, dto):
+        Rac, tac, Rbc, tbc = ctx.saved_tensors
+        Ra_s, ta_s, Rb_s, tb_s, rep, inverse, na = ctx.meta
+        dev = Rac.device
+        dRo = _f32c(dRo) if (dRo is not None and Rbc is not None) else None
+        dto = _f32c(dto) if (dto is not None and tbc is not None) else None
+        dRa = torch.empty_like(Rac)
+        dta = torch.empty_like(tac) if tac is not None else None
+        dRb = torch.empty_like(Rbc) if Rbc is not None else None
+        dtb = torch.empty_like(tbc) if tbc is not None else None
+        if na:
+            _check(lib().dfold_rot_compose_bwd(_ptr(Rac), _ptr(tac), _ptr(Rbc), _ptr(tbc), _ptr(dRo), _ptr(dto), _ptr(dRa), _ptr(dta),
+                                               _ptr(dRb), _ptr(dtb), na, rep, int(inverse), _stream()), "dfold_rot_compose_bwd")
+
+        def fit(g, shape):
+            if g is None or shape is None:
+                return None
+            return g.sum_to_size(shape) if tuple(g.shape) != tuple(shape) else g
+        return fit(dRa, Ra_s), fit(dta, ta_s), fit(dRb, Rb_s), fit(dtb, tb_s), None
+
+
+def rot_compose(Ra, ta, Rb, tb, inverse: bool = False):
+    """Rotation-matrix frames: returns (Ra Rb | None, Ra tb + ta | None); ``inverse``: Ra^T (tb - ta)."""
+    return _RotComposeFn.apply(Ra, ta, Rb, tb, inverse)

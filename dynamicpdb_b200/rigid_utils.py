@@ -26,6 +26,8 @@ from . import kernels as _k
 # --------------------------------------------------------------------------------------------------
 def rot_matmul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """[*,3,3] @ [*,3,3] written element-wise (no autocast down-casting). ref :22-79."""
+    if a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32:
+        return _k.rot_compose(a, None, b, None)[0]
     a0, a1, a2 = a.unbind(-2)  # rows of a: each [*,3]
     rows = []
     for ar in (a0, a1, a2):
@@ -36,6 +38,8 @@ def rot_matmul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def rot_vec_mul(r: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
     """[*,3,3] applied to [*,3]. ref :82-106."""
+    if r.is_cuda and t.is_cuda and r.dtype == torch.float32 and t.dtype == torch.float32:
+        return _k.rot_compose(r, None, None, t)[1]
     x, y, z = t[..., 0:1], t[..., 1:2], t[..., 2:3]
     return r[..., :, 0] * x + r[..., :, 1] * y + r[..., :, 2] * z
 
@@ -102,6 +106,8 @@ def rot_to_quat(rot: torch.Tensor) -> torch.Tensor:
 
 def quat_multiply(quat1: torch.Tensor, quat2: torch.Tensor) -> torch.Tensor:
     """Hamilton product. ref :254-263."""
+    if quat1.is_cuda and quat2.is_cuda and quat1.dtype == torch.float32 and quat2.dtype == torch.float32:
+        return _k.quat_mul(quat1, quat2)
     a1, b1, c1, d1 = quat1.unbind(-1)
     a2, b2, c2, d2 = quat2.unbind(-1)
     return torch.stack(
@@ -117,6 +123,8 @@ def quat_multiply(quat1: torch.Tensor, quat2: torch.Tensor) -> torch.Tensor:
 
 def quat_multiply_by_vec(quat: torch.Tensor, vec: torch.Tensor) -> torch.Tensor:
     """quat * (0, vec). ref :266-275."""
+    if quat.is_cuda and vec.is_cuda and quat.dtype == torch.float32 and vec.dtype == torch.float32:
+        return _k.quat_mul(quat, vec, b_is_vec=True)
     a, b, c, d = quat.unbind(-1)
     x, y, z = vec.unbind(-1)
     return torch.stack(
@@ -378,6 +386,8 @@ class Rigid:
         quats = self._rots._quats
         if quats is not None and quats.is_cuda and pts.is_cuda and pts.dtype == torch.float32:
             return _k.rigid_apply(quats, self._trans, pts, inverse=False)
+        if quats is None and pts.is_cuda and pts.dtype == torch.float32:
+            return _k.rot_compose(self._rots.get_rot_mats(), self._trans, None, pts)[1]
         return self._rots.apply(pts) + self._trans
 
     def invert_apply(self, pts: torch.Tensor) -> torch.Tensor:
@@ -385,10 +395,16 @@ class Rigid:
         quats = self._rots._quats
         if quats is not None and quats.is_cuda and pts.is_cuda and pts.dtype == torch.float32:
             return _k.rigid_apply(quats, self._trans, pts, inverse=True)
+        if quats is None and pts.is_cuda and pts.dtype == torch.float32:
+            return _k.rot_compose(self._rots.get_rot_mats(), self._trans, None, pts, inverse=True)[1]
         return self._rots.invert_apply(pts - self._trans)
 
     # -- the rest ----------------------------------------------------------------------------------
     def compose(self, r: "Rigid"):
+        """self o r: (R1 R2, R1 t2 + t1), ref :1065-1079 (one kernel on CUDA)."""
+        if self._trans.is_cuda and r._trans.is_cuda:
+            rot, trans = _k.rot_compose(self._rots.get_rot_mats(), self._trans, r._rots.get_rot_mats(), r._trans)
+            return Rigid(Rotation(rot_mats=rot), trans)
         return Rigid(self._rots.compose_r(r._rots), self._rots.apply(r._trans) + self._trans)
 
     def compose_r(self, rot: Rotation, order: str = "right"):

@@ -12,6 +12,7 @@ passed instead; this class exists so bench / tests run where /root/reference is 
 import numpy as np
 import torch
 
+from . import kernels as K
 from . import rigid_utils as ru
 
 
@@ -24,15 +25,42 @@ class SE3ScoreDiffuser:
         self._grid_np = self._sigma_np(np.linspace(0.0, 1.0, self.num_sigma))      # discrete_sigma, so3_diffuser.py:183
         self._grid = {}
 
+    @classmethod
+    def from_reference(cls, diffuser):
+        """Device-resident twin of a reference ``SE3Diffuser`` (src/data/se3_diffuser.py:31-45): same schedules, read from
+        the object's own sub-diffusers.  Returns None when `diffuser` is not shaped like one, or uses the cached-score
+        lookup (so3_diffuser.py:288-295), which this class does not mirror."""
+        so3, r3 = getattr(diffuser, "_so3_diffuser", None), getattr(diffuser, "_r3_diffuser", None)
+        try:
+            if so3 is None or r3 is None or so3.use_cached_score or so3.schedule != "logarithmic":
+                return None
+            from types import SimpleNamespace
+            conf = SimpleNamespace(
+                so3=SimpleNamespace(min_sigma=so3.min_sigma, max_sigma=so3.max_sigma, num_sigma=so3.num_sigma),
+                r3=SimpleNamespace(min_b=r3.min_b, max_b=r3.max_b, coordinate_scaling=r3._r3_conf.coordinate_scaling))
+            return cls(conf)
+        except AttributeError:
+            return None
+
+    def grid(self, device) -> torch.Tensor:
+        if device not in self._grid:
+            self._grid[device] = torch.from_numpy(self._grid_np).to(device)
+        return self._grid[device]
+
+    def fused_scores(self, rigids_t, rigids_pred, t, mask, ipa_coordinate_scaling: float):
+        """Both masked scores of the trunk epilogue (ipa_pytorch_dynamic.py:883-897) in ONE kernel launch
+        (csrc/epilogue.cu `score_fwd_kernel`, K9).  `rigids_pred` holds the translation BEFORE unscaling."""
+        q_t, q_p = rigids_t.get_rots().get_quats(), rigids_pred.get_rots().get_quats()
+        return K.score_epilogue(q_p, q_t, rigids_pred.get_trans(), rigids_t.get_trans(), t, self.grid(q_p.device), mask,
+                                max_sigma=self.max_sigma, min_sigma=self.min_sigma, min_b=self.min_b, max_b=self.max_b,
+                                r3_scale=self.coordinate_scaling, ipa_scale=ipa_coordinate_scaling, L=self.L)
+
     def _sigma_np(self, t):
         return np.log(t * np.exp(self.max_sigma) + (1 - t) * np.exp(self.min_sigma))   # :192-199 (logarithmic)
 
     def _sigma_of(self, t: torch.Tensor) -> torch.Tensor:
         """sigma(t) snapped to the reference's 1000-point grid: discrete_sigma[digitize(sigma(t)) - 1]."""
-        dev = t.device
-        if dev not in self._grid:
-            self._grid[dev] = torch.from_numpy(self._grid_np).to(dev)
-        grid = self._grid[dev]
+        grid = self.grid(t.device)
         t64 = t.to(torch.float64)
         s = torch.log(t64 * float(np.exp(self.max_sigma)) + (1 - t64) * float(np.exp(self.min_sigma)))
         idx = torch.bucketize(s, grid, right=True) - 1
@@ -40,6 +68,13 @@ class SE3ScoreDiffuser:
 
     # ---- se3_diffuser.py:119-125 ----
     def calc_rot_score(self, rots_t, rots_0, t, eps: float = 1e-6):
+        q_t, q_0 = rots_t.get_quats(), rots_0.get_quats()
+        if q_t.is_cuda and eps == 1e-6:
+            shp = torch.broadcast_shapes(q_t.shape, q_0.shape)
+            rot, _ = K.score_epilogue(q_0.expand(shp), q_t.expand(shp), None, None, t, self.grid(q_t.device), None, max_sigma=self.max_sigma, min_sigma=self.min_sigma,
+                                      min_b=self.min_b, max_b=self.max_b, r3_scale=1.0, ipa_scale=1.0, L=self.L)
+            return rot
+        # host-side tensors (callers outside the model: data pipeline, CPU tests): the same arithmetic in torch
         quats_0_inv = rots_0.invert().get_quats()
         quats_0t = ru.quat_multiply(quats_0_inv, rots_t.get_quats())
         vec = _quat_to_rotvec(quats_0t)

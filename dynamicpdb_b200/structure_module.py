@@ -180,12 +180,12 @@ class StructureModule(nn.Module):
             backb_to_global = Rigid(Rotation(rot_mats=rigids.get_rots().get_rot_mats(), quats=None),
                                     rigids.get_trans()).scale_translation(self.trans_scale_factor)
             unnormalized_angles, angles = self.angle_resnet(s, s_initial)
-            all_frames_to_global = self.torsion_angles_to_frames(backb_to_global, angles, aatype)
-            pred_xyz = self.frames_and_literature_positions_to_atom14_pos(all_frames_to_global, aatype)
+            # torsion_angles_to_frames + frames_and_literature_positions_to_atom14_pos (:716-727) in one kernel
+            pred_xyz, _, sidechain_frames = _feats.frames_to_atoms(backb_to_global, angles, aatype, want_frames=True)
             scaled_rigids = rigids.scale_translation(self.trans_scale_factor)
             outputs.append({
                 "frames": scaled_rigids.to_tensor_7(),
-                "sidechain_frames": all_frames_to_global.to_tensor_4x4(),
+                "sidechain_frames": sidechain_frames,
                 "unnormalized_angles": unnormalized_angles,
                 "angles": angles,
                 "positions": pred_xyz,

@@ -192,6 +192,52 @@ int dfold_ipa_ds_bwd(const float* logit0, long logit0_fstride, const float* q_pt
                      int dfold, float inf, float eps, const float* dcat, const float* d_og, const float* delta,
                      const float* dP, const float* Tz, float* dS, float* dgamma, float* dq_pts, float* dkv_pts, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Score epilogue (csrc/epilogue.cu), one warp per residue, no [n,L] temporaries, no host synchronisation.
+ * Replaces src/data/se3_diffuser.py:115-125 (calc_trans_score / calc_rot_score), src/data/utils.py:589-606
+ * (quat_to_rotvec), src/data/so3_diffuser.py:274-305 (torch_score, use_cached_score=False) -> :9-49 (igso3_expansion),
+ * :71-117 (score), :192-199 + :183-190 (sigma(t) snapped to the discrete grid, done on the device instead of
+ * du.move_to_np(t)), src/data/r3_diffuser.py:42,169-177.
+ *   q_pred / q_t [n,4] (w,x,y,z): predicted (rots_0) and noised (rots_t) rotations; x_pred / x_t [n,3] translations,
+ *   x_pred BEFORE the model's unscale (divided by ipa_scale inside); t: DEVICE double scalar; sigma_grid [G] doubles;
+ *   mask [n] or NULL.  rot_score [n,3] double; trans_score [n,3] double (trans_is_f64) or float.  Either output may be
+ *   NULL.  Backward: d_rot_score / d_trans_score may be NULL (treated as zero); dq_pred [n,4], dx_pred [n,3].
+ * ---------------------------------------------------------------------------------------------------------- */
+int dfold_score_fwd(const float* q_pred, const float* q_t, const float* x_pred, const float* x_t, const double* t,
+                    const double* sigma_grid, int G, double max_sigma, double min_sigma, double min_b, double max_b,
+                    float r3_scale, float ipa_scale, const float* mask, int L, long n,
+                    double* rot_score, void* trans_score, int trans_is_f64, void* stream);
+int dfold_score_bwd(const float* q_pred, const float* q_t, const float* x_pred, const float* x_t, const double* t,
+                    const double* sigma_grid, int G, double max_sigma, double min_sigma, double min_b, double max_b,
+                    float r3_scale, float ipa_scale, const float* mask, int L, long n,
+                    const double* d_rot_score, const void* d_trans_score, int trans_is_f64,
+                    float* dq_pred, float* dx_pred, void* stream);
+
+/* Structure epilogue: backbone frame o per-residue-type default frames o torsion rotations -> 8 rigid groups ->
+ * idealised atom14 -> atom37 (openfold/utils/feats.py:165-228, src/data/all_atom.py:114-154,
+ * src/model/Dfold_network_dynamic.py:574-594).  rot: [n,4] quaternion (un-normalised allowed: |q|^2 R, as
+ * quat_to_rot) or, rot_is_matrix, [n,9]; alpha [n,7,2] (sin, cos); aatype [n] int64; tables as dumped from
+ * openfold/np/residue_constants.py.  Outputs (each may be NULL): frames44 [n,8,4,4], atom14 [n,14,3], atom37 [n,37,3]. */
+int dfold_frames_to_atoms_fwd(const float* rot, int rot_is_matrix, const float* trans, const float* alpha, const long* aatype,
+                              const float* default_frames, const long* atom14_group, const float* atom14_mask,
+                              const float* atom14_pos, const long* atom37_to_atom14, const float* atom37_mask,
+                              float* frames44, float* atom14, float* atom37, long n, void* stream);
+
+/* Quaternion product a (x) b (openfold/utils/rigid_utils.py:254-263); b_is_vec: b is [n,3], the pure quaternion (0, v)
+ * (:266-275).  Backward: da = g (x) conj(b), db = conj(a) (x) g; da / db may be NULL. */
+int dfold_quat_mul_fwd(const float* a, const float* b, float* out, long n, int b_is_vec, void* stream);
+int dfold_quat_mul_bwd(const float* a, const float* b, const float* dout, float* da, float* db, long n, int b_is_vec, void* stream);
+/* Rotation-matrix frames: for every left frame ia < n_a and its `rep` consecutive right operands ib = ia*rep + j
+ *   rot_out[ib] = rot_a[ia] rot_b[ib]                 (rot_b / rot_out may be NULL)
+ *   trans_out[ib] = rot_a[ia] trans_b[ib] + trans_a[ia]   (inverse: rot_a^T (trans_b - trans_a); trans_* may be NULL)
+ * = rot_matmul :22, rot_vec_mul :82, Rotation.compose_r/apply/invert_apply :618-702, Rigid.compose :1065,
+ * Rigid.apply / invert_apply :1104-1130 and the translation of Rigid.invert :1132. */
+int dfold_rot_compose_fwd(const float* rot_a, const float* trans_a, const float* rot_b, const float* trans_b,
+                          float* rot_out, float* trans_out, long n_a, int rep, int inverse, void* stream);
+int dfold_rot_compose_bwd(const float* rot_a, const float* trans_a, const float* rot_b, const float* trans_b,
+                          const float* drot_out, const float* dtrans_out, float* drot_a, float* dtrans_a,
+                          float* drot_b, float* dtrans_b, long n_a, int rep, int inverse, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

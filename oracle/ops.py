@@ -95,5 +95,54 @@ def ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, *, 
     return torch.cat(feats, dim=-1)
 
 
-ALL = ["linear", "conv5x5", "global_layernorm", "layer_norm", "quat_to_rot", "rigid_apply", "ipa_points",
+def score_epilogue(q_pred, q_t, x_pred, x_t, t, grid, mask, *, max_sigma, min_sigma, min_b, max_b, r3_scale, ipa_scale, L=1000):
+    """K9: masked rotation (fp64) and translation scores; x_pred is the translation before unscaling."""
+    from types import SimpleNamespace
+    dc = SimpleNamespace(num_sigma=grid.numel(), min_sigma=min_sigma, max_sigma=max_sigma, L=L, min_b=min_b, max_b=max_b,
+                         coordinate_scaling=r3_scale)
+    m = 1.0 if mask is None else mask[..., None]
+    rs = O.rot_score(q_t, q_pred, t, dc) * m
+    if x_pred is None:
+        return rs, None
+    tt = t.reshape(-1)[:1][:, None, None] if x_pred.dim() == 3 else t.reshape(-1)[:1]
+    ts = O.trans_score(x_t, x_pred / ipa_scale, tt, dc) * m
+    return rs, ts
+
+
+def frames_to_atoms(rot, trans, alpha, aatype, tables, eager, want_frames=False, rot_is_matrix=False):
+    """K10: torsion frames -> atom14 -> atom37 (homogeneous 4x4 statement of the oracle)."""
+    if rot_is_matrix:
+        bb = rot.new_zeros(rot.shape[:-2] + (4, 4))
+        bb[..., :3, :3] = rot
+        bb[..., :3, 3] = trans
+        bb[..., 3, 3] = 1
+        fr = O.torsion_angles_to_frames(None, alpha.to(rot.dtype), aatype, bb44=bb)
+    else:
+        fr = O.torsion_angles_to_frames(torch.cat([rot, trans], dim=-1), alpha.to(rot.dtype), aatype)
+    a14 = O.frames_to_atom14(fr, aatype)
+    a37, _ = O.atom14_to_atom37(a14, aatype)
+    return (a14, a37, fr) if want_frames else (a14, a37)
+
+
+def quat_mul(a, b, b_is_vec=False):
+    if b_is_vec:
+        b = torch.cat([torch.zeros_like(b[..., :1]), b], dim=-1)
+    return O.quat_mul(a, b)
+
+
+def rot_compose(Ra, ta, Rb, tb, inverse=False):
+    Ro = Ra @ Rb if Rb is not None else None
+    to = None
+    if tb is not None:
+        if inverse:
+            d = tb - ta if ta is not None else tb
+            to = torch.einsum("...ba,...b->...a", Ra, d)
+        else:
+            to = torch.einsum("...ab,...b->...a", Ra, tb)
+            if ta is not None:
+                to = to + ta
+    return Ro, to
+
+
+ALL = ["score_epilogue", "frames_to_atoms", "quat_mul", "rot_compose", "linear", "conv5x5", "global_layernorm", "layer_norm", "quat_to_rot", "rigid_apply", "ipa_points",
        "compose_q_update", "keep_last_frame", "qk_logits", "ipa_attention"]

@@ -120,7 +120,7 @@ def test_c_abi_exports_every_declared_symbol():
 
 
 def test_ctypes_signatures_match_the_header():
-    """kernels._SIGS (p pointer, l long, i int, f float) must agree, argument by argument, with include/dfold_b200.h."""
+    """kernels._SIGS (p pointer, l long, i int, f float, d double) must agree, argument by argument, with include/dfold_b200.h."""
     header = open(os.path.join(ROOT, "include", "dfold_b200.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     for name, args in re.findall(r"\bint\s+(dfold_\w+)\s*\((.*?)\)\s*;", header, flags=re.S):
@@ -128,7 +128,7 @@ def test_ctypes_signatures_match_the_header():
         for a in [x.strip() for x in args.split(",")]:
             if a == "void":
                 continue
-            sig += "p" if "*" in a else ("l" if a.startswith("long") else ("i" if a.startswith("int") else ("f" if a.startswith("float") else "?")))
+            sig += "p" if "*" in a else ("l" if a.startswith("long") else ("i" if a.startswith("int") else ("f" if a.startswith("float") else ("d" if a.startswith("double") else "?"))))
         assert kernels._SIGS[name] == sig, (name, kernels._SIGS[name], sig)
 
 

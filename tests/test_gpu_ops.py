@@ -205,3 +205,105 @@ def test_conv5x5_cropped(F, N, Ci, Co, crop, relu, res):
         with torch.no_grad():
             wmask = _safe_gate(O.conv5x5(*[t.double() for t in inputs], relu=False, crop=crop))
     check("conv5x5", inputs, 1e-4, wmask=wmask, relu=relu, residual=residual, crop=crop)
+
+
+# --------------------------------------------------------------------------------------------------
+# epilogue kernels (csrc/epilogue.cu): K9 score epilogue, K10 frames -> atoms, quaternion / rotation-matrix algebra
+# --------------------------------------------------------------------------------------------------
+def _grid():
+    import numpy as np
+    g = np.log(np.linspace(0.0, 1.0, 1000) * np.exp(1.5) + (1 - np.linspace(0.0, 1.0, 1000)) * np.exp(0.1))
+    return torch.from_numpy(g)
+
+
+@pytest.mark.parametrize("tval,tdtype", [(0.03, torch.float64), (0.5, torch.float64), (1.0, torch.float32), (0.2, torch.float32)])
+def test_score_epilogue(tval, tdtype):
+    """K9 against the oracle in the reference's own arithmetic (fp32 trigonometry, fp64 series): rot_score fp64 at 1e-4
+    per residue (the north-star bar), gradients of both scores w.r.t. the predicted frame."""
+    F, N = 3, 70
+    gen = torch.Generator().manual_seed(5)
+    q_pred = torch.randn(F, N, 4, generator=gen) * 1.2           # non-unit on purpose
+    # noised rotation: some close to the prediction (small angles, incl. the small-angle branch), some far
+    q_t = torch.nn.functional.normalize(q_pred + torch.randn(F, N, 4, generator=gen) * torch.logspace(-5, 0.5, N)[None, :, None], dim=-1)
+    x_pred, x_t = torch.randn(F, N, 3, generator=gen) * 8, torch.randn(F, N, 3, generator=gen)
+    mask = (torch.rand(F, N, generator=gen) > 0.2).float()
+    t = torch.tensor([tval], dtype=tdtype)
+    kw = dict(max_sigma=1.5, min_sigma=0.1, min_b=0.1, max_b=20.0, r3_scale=0.1, ipa_scale=2.0, L=1000)
+    w_r = torch.randn(F, N, 3, generator=gen, dtype=torch.float64)
+    w_t = torch.randn(F, N, 3, generator=gen, dtype=torch.float64)
+
+    def run(fn, dev):
+        qp = q_pred.to(dev).requires_grad_(True)
+        xp = x_pred.to(dev).requires_grad_(True)
+        rs, ts = fn(qp, q_t.to(dev), xp, x_t.to(dev), t.to(dev), _grid().to(dev), mask.to(dev), **kw)
+        loss = (rs * w_r.to(dev)).sum() + (ts.double() * w_t.to(dev)).sum()
+        gq, gx = torch.autograd.grad(loss, [qp, xp])
+        return rs.detach().cpu(), ts.detach().cpu(), gq.cpu(), gx.cpu()
+
+    ro, to_, gqo, gxo = run(O.score_epilogue, "cpu")
+    rk, tk, gqk, gxk = run(K.score_epilogue, DEV)
+    assert rk.dtype == torch.float64 and tk.dtype == to_.dtype
+    assert (ro - rk).norm(dim=-1).max().item() < 1e-4 * max(1.0, ro.norm(dim=-1).max().item())
+    assert _rel_err(to_.double(), tk.double()) < 2e-6
+    assert _rel_err(gxo.double(), gxk.double()) < 2e-6
+    assert _rel_err(gqo.double(), gqk.double()) < 2e-4, _rel_err(gqo.double(), gqk.double())
+    # rotation score alone (the diffuser API, calc_rot_score)
+    r2, none = K.score_epilogue(q_pred.to(DEV), q_t.to(DEV), None, None, t.to(DEV), _grid().to(DEV), None, **kw)
+    assert none is None and (r2.cpu() * mask[..., None] - rk).abs().max().item() < 1e-12 * max(1.0, rk.abs().max().item())
+
+
+@pytest.mark.parametrize("is_mat,want_frames", [(False, False), (True, True), (False, True)])
+def test_frames_to_atoms(is_mat, want_frames):
+    from dynamicpdb_b200 import feats as FT
+    from dynamicpdb_b200 import rigid_utils as ru
+    F, N = 2, 45
+    gen = torch.Generator().manual_seed(9)
+    quat = torch.randn(F, N, 4, generator=gen)
+    quat = quat / quat.norm(dim=-1, keepdim=True) * (1.0 + 0.05 * torch.randn(F, N, 1, generator=gen))    # slightly non-unit
+    trans = torch.randn(F, N, 3, generator=gen) * 10
+    alpha = torch.nn.functional.normalize(torch.randn(F, N, 7, 2, generator=gen), dim=-1) * 1.1
+    aatype = torch.randint(0, 21, (F, N), generator=gen)
+    rot = O.quat_to_rot(quat) if is_mat else quat
+    gws = None
+
+    def run(dev, product):
+        nonlocal gws
+        r_ = rot.to(dev).requires_grad_(True)
+        t_ = trans.to(dev).requires_grad_(True)
+        a_ = alpha.to(dev).requires_grad_(True)
+        if product:
+            rots = ru.Rotation(rot_mats=r_) if is_mat else ru.Rotation(quats=r_, normalize_quats=False)
+            outs = FT.frames_to_atoms(ru.Rigid(rots, t_), a_, aatype.to(dev), want_frames=want_frames)
+        else:
+            outs = O.frames_to_atoms(r_.double(), t_.double(), a_.double(), aatype, None, None, want_frames, is_mat)
+        if gws is None:
+            gws = [torch.randn(o.shape, generator=gen, dtype=torch.float64) for o in outs]
+        loss = sum((o.double() * w.to(dev)).sum() for o, w in zip(outs, gws))
+        grads = torch.autograd.grad(loss, [r_, t_, a_])
+        return [o.detach().double().cpu() for o in outs], [g.double().cpu() for g in grads]
+
+    oo, og = run("cpu", False)
+    ko, kg = run(DEV, True)
+    for a, b in zip(oo, ko):
+        assert a.shape == b.shape and _rel_err(a, b) < 2e-6
+    for a, b in zip(og, kg):
+        assert _rel_err(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("b_is_vec", [False, True])
+def test_quat_mul(b_is_vec):
+    check("quat_mul", [R(3, 20, 4), R(3, 20, 3 if b_is_vec else 4)], 2e-6, b_is_vec=b_is_vec)
+    check("quat_mul", [R(1, 20, 4), R(3, 1, 3 if b_is_vec else 4)], 2e-6, b_is_vec=b_is_vec)      # broadcast both ways
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_rot_compose(inverse):
+    first = lambda out, *a: out[0]
+    second = lambda out, *a: out[1]
+    # rotation product, frame composition, point application with a trailing broadcast (r[..., None].apply(pts))
+    check("rot_compose", [R(3, 20, 3, 3), None, R(3, 20, 3, 3), None], 2e-6, post=first)
+    if not inverse:
+        check("rot_compose", [R(3, 20, 3, 3), R(3, 20, 3), R(3, 20, 3, 3), R(3, 20, 3)], 2e-6)
+        check("rot_compose", [R(3, 20, 1, 3, 3), R(3, 20, 1, 3), R(3, 20, 8, 3, 3), R(3, 20, 8, 3)], 2e-6)
+    check("rot_compose", [R(3, 20, 1, 3, 3), R(3, 20, 1, 3), None, R(3, 20, 17, 3)], 2e-6, post=second, inverse=inverse)
+    check("rot_compose", [R(20, 3, 3), None, None, R(3, 20, 3)], 2e-6, post=second, inverse=inverse)        # leading broadcast
