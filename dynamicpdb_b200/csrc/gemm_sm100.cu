@@ -22,6 +22,7 @@
 // Replaces (reference file:line): nn.Linear in src/model/ipa_pytorch_dynamic.py:284-305,757-796,590,
 // openfold/model/structure_module.py:102-110,58-59; nn.Conv2d stack src/model/ipa_pytorch_dynamic.py:664-706.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace dfold {
@@ -75,6 +76,9 @@ struct GemmParams {
     int b_n_zmul;           // B column offset    = zq * b_n_zmul
     int kb_per_split;       // k-blocks per K split
     int atomic;             // epilogue accumulates with atomicAdd (split-K)
+    int shift_on_a;         // pair kernel, mode 1: the tap shift / frame offset applies to operand A (roles swapped)
+    long o_rs, o_cs;        // pair kernel, mode 1: output element (row m, column n) at out[m * o_rs + n * o_cs]
+    long long* stats;       // debug (dfold_debug_gemm_stats): per CTA {total, MMA wait full, MMA wait acc_empty, acc warp wait} cycles
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -265,6 +269,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const bool mn_major = (p.mode == 1);
             if (mn_major) idesc |= (1u << 15) | (1u << 16);     // A and B are MN-major in weight-gradient mode
+            long long w_full = 0, w_acc = 0, t_begin = 0;
+            if (p.stats) t_begin = clock64();
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % Cfg::kStages;
                 const uint32_t ph = (kb / Cfg::kStages) & 1;
@@ -273,10 +279,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 const bool chunk_start = (kb % kChunk) == 0;
                 if (chunk_start) {
                     // the accumulate warps must have drained this TMEM buffer (two chunks ago)
+                    const long long t0 = p.stats ? clock64() : 0;
                     mbar_wait(acc_empty_bar(buf), ((chunk >> 1) & 1) ^ 1u);
+                    if (p.stats) w_acc += clock64() - t0;
                     tcgen05_fence_after();
                 }
-                mbar_wait(full_bar(s), ph);
+                {
+                    const long long t0 = p.stats ? clock64() : 0;
+                    mbar_wait(full_bar(s), ph);
+                    if (p.stats) w_full += clock64() - t0;
+                }
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
                 const uint32_t sa_hi = smem_base + s * Cfg::kStageBytes;
@@ -300,6 +312,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 if ((kb % kChunk) == kChunk - 1 || kb == num_kb - 1)
                     umma_commit(acc_full_bar(buf));   // this chunk's partial sum is complete
             }
+            if (p.stats) {
+                const long cta = ((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+                p.stats[4 * cta + 0] = clock64() - t_begin;
+                p.stats[4 * cta + 1] = w_full;
+                p.stats[4 * cta + 2] = w_acc;
+            }
         }
     } else {
         // =============================== accumulate + epilogue (warps 2..9) ===============================
@@ -310,9 +328,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
         for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
         const int nchunks = (num_kb + kChunk - 1) / kChunk;
+        long long w_accfull = 0;
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             const int buf = chunk & 1;
+            const long long t0 = p.stats ? clock64() : 0;
             mbar_wait(acc_full_bar(buf), (chunk >> 1) & 1);
+            if (p.stats) w_accfull += clock64() - t0;
             tcgen05_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < HALF; c0 += 32) {
@@ -324,6 +345,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty_bar(buf));
+        }
+        if (p.stats && warp == 2 && lane == 0) {
+            const long cta = ((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            p.stats[4 * cta + 3] = w_accfull;
         }
         const int r = q * 32 + lane;                    // row inside the tile
         long grow;                                      // global output row
@@ -380,6 +405,306 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster compute a 256 x BN tile.  Each CTA stages its own 128 rows of
+// A and HALF of the B tile (BN/2 rows) and the pair's tensor cores read both halves, so per SM the operand traffic per
+// MMA cycle halves compared with the single-CTA 128 x 128 tile: measured with dfold_debug_gemm_stats the single-CTA
+// kernel's MMA thread never waits on data yet issues at 65 % of the MMA floor — shared-memory bandwidth (operand reads
+// 128 B/clk + TMA writes 85 B/clk per SM) is the limiter.  Here: reads 64 B/clk + writes 42 B/clk (BN = 256).
+//   full[s]      lives in the LEADER CTA (rank 0): count 2 (one arrival per CTA's producer) + the bytes of both CTAs
+//   empty[s]     per CTA, released by the leader's MMA thread with a multicast tcgen05.commit
+//   acc_full[b]  per CTA (multicast commit); acc_empty[b] in the leader, count 16 (8 accumulate warps x 2 CTAs)
+// K-major operands only (forward / data-gradient / linear), no batching.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> rank 0
+
+template <int BN> struct PairCfg {
+    static constexpr int kBRows = BN / 2;                      // B rows staged per CTA
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = kBRows * BK * 2;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+    static constexpr int kStages = (212 * 1024) / kStageBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+    static_assert(kBBytes % 1024 == 0, "B half tile must be a whole number of swizzle atoms");
+    static_assert(BN % 32 == 0 && BN <= 256, "pair tile width");
+};
+
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar_leader) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 const GemmParams p) {
+    using Cfg = PairCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto acc_full_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + b); };
+    auto acc_empty_bar = [&](int b) { return bar_base + 8u * (2 * Cfg::kStages + 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const bool leader = rank == 0;
+
+    // ---- tile coordinates: the pair owns row tiles 2j, 2j+1 and one BN-wide column tile ----
+    const int m_tile = blockIdx.x;
+    const int n_tile = blockIdx.y;
+    const int zq = blockIdx.z;                                 // mode 1: tap
+    const int f0 = m_tile / p.tiles_per_frame;                 // mode 0; beyond the last frame for a padding CTA: loads zero-fill
+    const int n0 = (m_tile % p.tiles_per_frame) * BM;
+    const int m0 = m_tile * BM;                                // mode 1
+    const int col0 = n_tile * BN;
+    const int num_kb = p.num_kb;
+    const bool mn_major = p.mode == 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full_bar(b), 1); mbar_init(acc_empty_bar(b), 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // =============================== TMA producer (both CTAs) ===============================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::kStages;
+                const uint32_t ph = (kb / Cfg::kStages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                const uint32_t fb = full_bar(s) & kPeerMask;           // the leader's barrier
+                if (leader) mbar_expect_tx(full_bar(s), 2 * Cfg::kStageBytes);
+                const uint32_t sa_hi = smem_base + s * Cfg::kStageBytes;
+                const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                const uint32_t sb_hi = sa_lo + Cfg::kABytes;
+                const uint32_t sb_lo = sb_hi + Cfg::kBBytes;
+                if (!mn_major) {
+                    const int tap = kb / p.kc, c = kb % p.kc;
+                    const int dn = tap % p.taps_n - p.taps_n / 2;
+                    const int df = tap / p.taps_n - p.taps_f / 2;
+                    const int ak = c * BK;
+                    const int af = f0 + p.f_start + df;
+                    const int brow = col0 + (int)rank * Cfg::kBRows;
+                    tma_load_3d_pair(sa_hi, &map_a_hi, fb, ak, n0 + dn, af);
+                    tma_load_3d_pair(sa_lo, &map_a_lo, fb, ak, n0 + dn, af);
+                    tma_load_3d_pair(sb_hi, &map_b_hi, fb, ak, brow, tap);
+                    tma_load_3d_pair(sb_lo, &map_b_lo, fb, ak, brow, tap);
+                } else {
+                    // K = pixels (frame f, 64-residue block j); MN-major boxes of 64 channels x 64 residues.  The tap's
+                    // residue / frame shift sits on one operand's row coordinates (out-of-image rows zero-fill).
+                    const int f = kb / p.kc, j = kb % p.kc;
+                    const int dn = zq % p.taps_n - p.taps_n / 2;
+                    const int df = zq / p.taps_n - p.taps_f / 2;
+                    const int a_n = j * BK + (p.shift_on_a ? dn : 0), a_f = f + (p.shift_on_a ? p.b_f_add + df : 0);
+                    const int b_n = j * BK + (p.shift_on_a ? 0 : dn), b_f = f + (p.shift_on_a ? 0 : p.b_f_add + df);
+                    const int bn0 = col0 + (int)rank * Cfg::kBRows;
+#pragma unroll
+                    for (int a = 0; a < BM / 64; ++a) {
+                        tma_load_3d_pair(sa_hi + a * 8192, &map_a_hi, fb, m0 + a * 64, a_n, a_f);
+                        tma_load_3d_pair(sa_lo + a * 8192, &map_a_lo, fb, m0 + a * 64, a_n, a_f);
+                    }
+#pragma unroll
+                    for (int b = 0; b < Cfg::kBRows / 64; ++b) {
+                        tma_load_3d_pair(sb_hi + b * 8192, &map_b_hi, fb, bn0 + b * 64, b_n, b_f);
+                        tma_load_3d_pair(sb_lo + b * 8192, &map_b_lo, fb, bn0 + b * 64, b_n, b_f);
+                    }
+                }
+                if (!leader) mbar_arrive_leader(full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer (leader CTA only) ===============================
+        if (leader && lane == 0) {
+            // D=f32, A=B=bf16, N=BN, M=256 across the pair; K-major operands, or MN-major in weight-gradient mode
+            uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            if (mn_major) idesc |= (1u << 15) | (1u << 16);
+            long long w_full = 0, w_acc = 0, t_begin = 0;
+            if (p.stats) t_begin = clock64();
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::kStages;
+                const uint32_t ph = (kb / Cfg::kStages) & 1;
+                const int chunk = kb / kChunk;
+                const int buf = chunk & 1;
+                const bool chunk_start = (kb % kChunk) == 0;
+                if (chunk_start) {
+                    const long long t0 = p.stats ? clock64() : 0;
+                    mbar_wait(acc_empty_bar(buf), ((chunk >> 1) & 1) ^ 1u);
+                    if (p.stats) w_acc += clock64() - t0;
+                    tcgen05_fence_after();
+                }
+                {
+                    const long long t0 = p.stats ? clock64() : 0;
+                    mbar_wait(full_bar(s), ph);
+                    if (p.stats) w_full += clock64() - t0;
+                }
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                const uint32_t sa_hi = smem_base + s * Cfg::kStageBytes;
+                const uint32_t sa_lo = sa_hi + Cfg::kABytes;
+                const uint32_t sb_hi = sa_lo + Cfg::kABytes;
+                const uint32_t sb_lo = sb_hi + Cfg::kBBytes;
+                const uint64_t da_hi = mn_major ? make_sw128_mn_desc(sa_hi) : make_sw128_desc(sa_hi);
+                const uint64_t da_lo = mn_major ? make_sw128_mn_desc(sa_lo) : make_sw128_desc(sa_lo);
+                const uint64_t db_hi = mn_major ? make_sw128_mn_desc(sb_hi) : make_sw128_desc(sb_hi);
+                const uint64_t db_lo = mn_major ? make_sw128_mn_desc(sb_lo) : make_sw128_desc(sb_lo);
+                const uint64_t kstep = mn_major ? (uint64_t)((2 * 1024) >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t koff = kstep * k;
+                    umma_bf16_pair(tmem_d, da_lo + koff, db_hi + koff, idesc, (!chunk_start || k > 0) ? 1u : 0u);
+                    umma_bf16_pair(tmem_d, da_hi + koff, db_lo + koff, idesc, 1u);
+                    umma_bf16_pair(tmem_d, da_hi + koff, db_hi + koff, idesc, 1u);
+                }
+                umma_commit_pair(empty_bar(s));
+                if ((kb % kChunk) == kChunk - 1 || kb == num_kb - 1) umma_commit_pair(acc_full_bar(buf));
+            }
+            if (p.stats) {
+                const long cta = ((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+                p.stats[4 * cta + 0] = clock64() - t_begin;
+                p.stats[4 * cta + 1] = w_full;
+                p.stats[4 * cta + 2] = w_acc;
+            }
+        }
+    } else {
+        // =============================== accumulate + epilogue (warps 2..9, both CTAs) ===============================
+        constexpr int HALF = BN / 2;
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float acc[HALF];
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+        const int nchunks = (num_kb + kChunk - 1) / kChunk;
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            const int buf = chunk & 1;
+            mbar_wait(acc_full_bar(buf), (chunk >> 1) & 1);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF + c0), v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(v[i]);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(acc_empty_bar(buf));
+        }
+        const int r = q * 32 + lane;
+        if (mn_major) {
+            // weight gradient: row = channel m0 + r; element (m, n) at out[zq * tap_stride + m * o_rs + n * o_cs]
+            // (o_rs = 1 for swapped operand roles: the 32 lanes of a warp then write 32 consecutive floats)
+            const long gm = (long)m0 + r;
+            if (gm < p.out_rows) {
+                float* ob = p.out + (long)zq * p.out_tap_stride + gm * p.o_rs;
+                const bool v4 = p.o_cs == 1 && ((p.o_rs & 3) == 0) && ((p.out_tap_stride & 3) == 0) &&
+                                ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+                if (v4) {
+#pragma unroll
+                    for (int c = 0; c < HALF; c += 4) {
+                        const int gc = col0 + half * HALF + c;
+                        if (gc + 4 <= p.n_out)
+                            *reinterpret_cast<float4*>(ob + gc) = make_float4(acc[c] * p.alpha, acc[c + 1] * p.alpha, acc[c + 2] * p.alpha, acc[c + 3] * p.alpha);
+                        else
+                            for (int i = 0; i < 4; ++i)
+                                if (gc + i < p.n_out) ob[gc + i] = acc[c + i] * p.alpha;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < HALF; ++c) {
+                        const int gc = col0 + half * HALF + c;
+                        if (gc < p.n_out) ob[(long)gc * p.o_cs] = acc[c] * p.alpha;
+                    }
+                }
+            }
+        }
+        const int n = n0 + r;
+        const long grow = (long)f0 * p.Nr + n;
+        const bool row_ok = !mn_major && (n < p.Nr) && (grow < p.out_rows);
+        float* orow = p.out + grow * p.ldo;
+        const float* rrow = p.res ? p.res + grow * p.ldr : nullptr;
+        const bool vec_ok = ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        if (row_ok) {
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 4) {
+                const int gc0 = col0 + half * HALF + c0;
+                if (gc0 >= p.n_out) break;
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float x = acc[c0 + i] * p.alpha;
+                    const int gc = gc0 + i;
+                    if (gc < p.n_out) {
+                        if (p.bias) x += __ldg(p.bias + gc);
+                        if (p.act == 1) x = fmaxf(x, 0.f);
+                        else if (p.act == 2) x = x / (1.f + __expf(-x));
+                        if (rrow) x += p.beta * __ldg(rrow + gc);
+                    }
+                    o[i] = x;
+                }
+                if (vec_ok && gc0 + 4 <= p.n_out) {
+                    *reinterpret_cast<float4*>(orow + gc0) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (gc0 + i < p.n_out) orow[gc0 + i] = o[i];
+                }
+            }
+        }
+        tcgen05_fence_before();
+    }
+    // the peer's tensor core reads this CTA's B half and (leader) both CTAs' barriers: leave together
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmemCols));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ---------------------------------------------------------------------------------------------------
@@ -417,20 +742,17 @@ int make_map(CUtensorMap* m, const void* base, long d0, long d1, long d2, long s
     return 0;
 }
 
+long long* g_stats = nullptr;      // set by dfold_debug_gemm_stats
+
 template <int BN>
-int launch(const CUtensorMap* maps, const GemmParams& p, dim3 grid, cudaStream_t st) {
+int launch(const CUtensorMap* maps, const GemmParams& p_in, dim3 grid, cudaStream_t st) {
     using Cfg = TileCfg<BN>;
+    GemmParams p = p_in;
+    p.stats = g_stats;
     static SmemCfg cfg;
     if (ensure_dyn_smem(gemm_bf16x3_kernel<BN>, Cfg::kSmemBytes, cfg, "gemm_bf16x3_kernel")) return 1;
     gemm_bf16x3_kernel<BN><<<grid, NTHREADS, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p);
     return check_launch("gemm_bf16x3_kernel");
-}
-
-void default_batching(GemmParams& p) {
-    p.bmod = 1; p.a_f_div = 1; p.a_k_bstride = 0; p.b_k_ofs = 0; p.b_k_bstride = 0; p.b_z_bstride = 0;
-    p.o_f_div = 1; p.o_col_bstride = 0; p.f_start = 0; p.b_f_add = 0;
-    p.zdiv = 1; p.a_f_mul = 1; p.a_z_mul = 0; p.b_f_mul = 1; p.b_z_mul = 0; p.b_n_zmul = 0;
-    p.kb_per_split = p.num_kb; p.atomic = 0;
 }
 
 int sm_count() {
@@ -443,6 +765,41 @@ int sm_count() {
     }
     return n[dev];
 }
+
+template <int BN>
+int launch_pair(const CUtensorMap* maps, const GemmParams& p_in, dim3 grid, cudaStream_t st) {
+    using Cfg = PairCfg<BN>;
+    static SmemCfg cfg;
+    if (ensure_dyn_smem(gemm_pair_kernel<BN>, Cfg::kSmemBytes, cfg, "gemm_pair_kernel")) return 1;
+    GemmParams p = p_in;
+    p.stats = g_stats;
+    gemm_pair_kernel<BN><<<grid, NTHREADS, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    return check_launch("gemm_pair_kernel");
+}
+
+// Width of the CTA-pair tile (0 = use the single-CTA kernel): the pair kernel needs a problem large enough to fill the
+// chip with 256-row tiles; among {256, 160} the width with the fewest (waves x width) wins (160 = 640 / 4 = 1280 / 8).
+int pick_pair_bn(long n_out, long row_tiles) {
+    const char* off = getenv("DFOLD_GEMM_NO_PAIR");
+    if (off && off[0] == '1') return 0;
+    if (n_out < 160 || row_tiles < 16) return 0;
+    const long pairs = cdiv(row_tiles, 2), slots = sm_count() / 2;
+    long best = 0, best_cost = 0;
+    const int widths[2] = {256, 160};
+    for (int w : widths) {
+        const long cost = cdiv(cdiv(n_out, w) * pairs, slots) * w;
+        if (best == 0 || cost < best_cost) { best = w; best_cost = cost; }
+    }
+    return (int)best;
+}
+
+void default_batching(GemmParams& p) {
+    p.bmod = 1; p.a_f_div = 1; p.a_k_bstride = 0; p.b_k_ofs = 0; p.b_k_bstride = 0; p.b_z_bstride = 0;
+    p.o_f_div = 1; p.o_col_bstride = 0; p.f_start = 0; p.b_f_add = 0;
+    p.zdiv = 1; p.a_f_mul = 1; p.a_z_mul = 0; p.b_f_mul = 1; p.b_z_mul = 0; p.b_n_zmul = 0;
+    p.kb_per_split = p.num_kb; p.atomic = 0;
+}
+
 
 // Tile width: every CTA owns one SM (192 KB of shared memory), so the launch runs in ceil(tiles / SMs) waves whose
 // duration is proportional to BN.  Pick the width with the smallest waves x BN (ties -> the wider tile, which re-reads
@@ -464,6 +821,13 @@ using namespace dfold;
 // ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
+// Development aid: when `buf` (device, 4 x int64 per CTA of the next launches) is non-null every GEMM launch records, per
+// CTA, the cycles of its mainloop and the cycles its MMA-issuing thread / accumulate warps spent waiting on barriers.
+extern "C" int dfold_debug_gemm_stats(long long* buf) {
+    g_stats = buf;
+    return 0;
+}
+
 extern "C" int dfold_gemm_bf16x3(
     const uint16_t* a_hi, const uint16_t* a_lo, long F, long F_out, int f_start, long Nr, long K, long lda,
     const uint16_t* b_hi, const uint16_t* b_lo, long n_out, long ldb, int taps_f, int taps_n,
@@ -472,14 +836,17 @@ extern "C" int dfold_gemm_bf16x3(
     DFOLD_REQUIRE(F > 0 && F_out > 0 && Nr > 0 && K > 0 && n_out > 0, "dfold_gemm_bf16x3: empty problem");
     DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dfold_gemm_bf16x3: lda/ldb must be multiples of 8 (got %ld, %ld)", lda, ldb);
     DFOLD_REQUIRE(taps_f >= 1 && taps_n >= 1 && (taps_f & 1) && (taps_n & 1), "dfold_gemm_bf16x3: tap grid must be odd");
-    const int bn = pick_bn(n_out, F_out * cdiv(Nr, BM));
+    const long row_tiles = F_out * cdiv(Nr, BM);
+    const int pbn = pick_pair_bn(n_out, row_tiles);
+    const int bn = pbn ? pbn : pick_bn(n_out, row_tiles);
     CUtensorMap maps[4];
-    // A: dims (K, Nr, F)   B: dims (K, n_out, taps)
+    // A: dims (K, Nr, F)   B: dims (K, n_out, taps); the pair kernel stages half a B tile per CTA
     if (make_map(&maps[0], a_hi, K, Nr, F, lda, Nr * lda, BK, BM, 1)) return 1;
     if (make_map(&maps[1], a_lo, K, Nr, F, lda, Nr * lda, BK, BM, 1)) return 1;
     const long taps = (long)taps_f * taps_n;
-    if (make_map(&maps[2], b_hi, K, n_out, taps, ldb, n_out * ldb, BK, bn, 1)) return 1;
-    if (make_map(&maps[3], b_lo, K, n_out, taps, ldb, n_out * ldb, BK, bn, 1)) return 1;
+    const int bbox = pbn ? pbn / 2 : bn;
+    if (make_map(&maps[2], b_hi, K, n_out, taps, ldb, n_out * ldb, BK, bbox, 1)) return 1;
+    if (make_map(&maps[3], b_lo, K, n_out, taps, ldb, n_out * ldb, BK, bbox, 1)) return 1;
     GemmParams p{};
     p.mode = 0;
     p.kc = (int)cdiv(K, BK);
@@ -494,8 +861,13 @@ extern "C" int dfold_gemm_bf16x3(
     p.alpha = alpha; p.beta = beta; p.act = act;
     default_batching(p);
     p.f_start = f_start;
-    dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(F_out * p.tiles_per_frame), 1);
     cudaStream_t st = as_stream(stream);
+    if (pbn) {
+        dim3 pgrid((unsigned)(2 * cdiv(row_tiles, 2)), (unsigned)cdiv(n_out, pbn), 1);
+        if (pbn == 256) return launch_pair<256>(maps, p, pgrid, st);
+        return launch_pair<160>(maps, p, pgrid, st);
+    }
+    dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(F_out * p.tiles_per_frame), 1);
     if (bn == 256) return launch<256>(maps, p, grid, st);
     if (bn == 128) return launch<128>(maps, p, grid, st);
     return launch<64>(maps, p, grid, st);
@@ -512,6 +884,43 @@ extern "C" int dfold_gemm_wgrad_bf16x3(
     float* out, long ldo, float alpha, void* stream) {
     DFOLD_REQUIRE(M > 0 && Nn > 0 && F > 0 && Fb > 0 && Nr > 0, "dfold_gemm_wgrad_bf16x3: empty problem");
     DFOLD_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "dfold_gemm_wgrad_bf16x3: lda/ldb must be multiples of 8 (got %ld, %ld)", lda, ldb);
+    // ---- CTA-pair path: 256 x {256,128} tiles; the operand whose channel count is an even number of 128-row tiles
+    //      takes the M role (swapping roles transposes the store, which the epilogue does with strides) ----
+    {
+        const char* off = getenv("DFOLD_GEMM_NO_PAIR");
+        const bool enabled = !(off && off[0] == '1');
+        const long mt = cdiv(M, BM), nt = cdiv(Nn, BM);
+        const bool swap = (mt % 2 != 0) && (nt % 2 == 0);
+        if (enabled && F * cdiv(Nr, BK) >= 32 && M >= 256 && Nn >= 128 && (mt % 2 == 0 || swap)) {
+            const long Mp = swap ? Nn : M, Np = swap ? M : Nn;
+            const int pbn = (Np % 256 == 0) ? 256 : 128;
+            const uint16_t *pa_hi = swap ? b_hi : a_hi, *pa_lo = swap ? b_lo : a_lo, *pb_hi = swap ? a_hi : b_hi, *pb_lo = swap ? a_lo : b_lo;
+            const long pa_ld = swap ? ldb : lda, pb_ld = swap ? lda : ldb, pa_F = swap ? Fb : F, pb_F = swap ? F : Fb;
+            CUtensorMap maps[4];
+            if (make_map(&maps[0], pa_hi, Mp, Nr, pa_F, pa_ld, Nr * pa_ld, 64, BK, 1)) return 1;
+            if (make_map(&maps[1], pa_lo, Mp, Nr, pa_F, pa_ld, Nr * pa_ld, 64, BK, 1)) return 1;
+            if (make_map(&maps[2], pb_hi, Np, Nr, pb_F, pb_ld, Nr * pb_ld, 64, BK, 1)) return 1;
+            if (make_map(&maps[3], pb_lo, Np, Nr, pb_F, pb_ld, Nr * pb_ld, 64, BK, 1)) return 1;
+            GemmParams p{};
+            p.mode = 1;
+            p.kc = (int)cdiv(Nr, BK);
+            p.num_kb = (int)(F * p.kc);
+            p.taps_n = taps_n; p.taps_f = taps_f;
+            p.tiles_per_frame = 1; p.Nr = (int)Nr;
+            p.out_rows = Mp; p.n_out = (int)Np;
+            p.out = out; p.ldo = ldo; p.out_tap_stride = M * ldo;
+            p.alpha = alpha; p.beta = 0.f; p.act = 0;
+            default_batching(p);
+            p.b_f_add = b_f_add;
+            p.shift_on_a = swap ? 1 : 0;
+            p.o_rs = swap ? 1 : ldo;
+            p.o_cs = swap ? ldo : 1;
+            dim3 pgrid((unsigned)(2 * cdiv(cdiv(Mp, BM), 2)), (unsigned)cdiv(Np, pbn), (unsigned)(taps_f * taps_n));
+            cudaStream_t st = as_stream(stream);
+            if (pbn == 256) return launch_pair<256>(maps, p, pgrid, st);
+            return launch_pair<128>(maps, p, pgrid, st);
+        }
+    }
     const int bn = pick_bn(Nn, cdiv(M, BM) * taps_f * taps_n);
     CUtensorMap maps[4];
     // dims (channel, residue, frame); boxes of 64 channels x 64 residues

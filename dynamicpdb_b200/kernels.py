@@ -25,6 +25,7 @@ _LIB = None
 _SIGS = {
     "dfold_abi_version": "",
     "dfold_capture_id": "pp",
+    "dfold_debug_gemm_stats": "p",
     "dfold_split2d": "plllipl" + "ppll" + "ppll" + "pp",
     "dfold_conv_weight_prep": "piii" + "ppl" + "ppl" + "p",
     "dfold_taps_to_param": "piiipp",

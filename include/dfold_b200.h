@@ -24,6 +24,10 @@ int dfold_abi_version(void);
 /* Host-side helper: *id_out = id of the CUDA-graph capture `stream` is recording into, 0 when not capturing
  * (HOST pointer). */
 int dfold_capture_id(void* stream, unsigned long long* id_out);
+/* Development aid: non-NULL `buf` (DEVICE, 4 x int64 per CTA) makes every following tcgen05 GEMM launch record per CTA
+ * {mainloop cycles, MMA-thread wait on operand stages, MMA-thread wait on accumulator drain, accumulate-warp wait};
+ * NULL switches it off. */
+int dfold_debug_gemm_stats(long long* buf);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Split-precision tensor-core GEMM (tcgen05, bf16 x 3, fp32 accumulate in TMEM) and its operand preparation.

@@ -71,7 +71,7 @@ def _record_gates(net, monkeypatch):
 def test_full_network_matches_oracle(name, preset, nf, N, monkeypatch):
     """Outputs and EVERY parameter gradient.  The oracle back-propagates through the ReLU gates the CUDA forward applied
     (oracle.set_gates), so a pre-activation within rounding of zero cannot gate differently on the two sides; the
-    gradient comparison then has no outlier allowance: relative L2 per parameter tensor <= 5e-3."""
+    gradient comparison then has no outlier allowance: relative L2 per parameter tensor <= 2e-3 (measured <= 1e-3)."""
     torch.manual_seed(0)
     conf = syn.model_conf(nf, **preset)
     dconf = syn.diffuser_conf(1.0)
@@ -141,4 +141,4 @@ def test_full_network_matches_oracle(name, preset, nf, N, monkeypatch):
     _record(name, errs)
     assert not problems, f"{name}: " + "; ".join(problems)
     assert errs["loss_rel"] < 1e-4
-    assert worst[1] < 5e-3, f"{name}: gradient of {worst[0]} rel L2 err {worst[1]:.3e}"
+    assert worst[1] < 2e-3, f"{name}: gradient of {worst[0]} rel L2 err {worst[1]:.3e}"

@@ -223,8 +223,11 @@ def test_score_epilogue(tval, tdtype):
     F, N = 3, 70
     gen = torch.Generator().manual_seed(5)
     q_pred = torch.randn(F, N, 4, generator=gen) * 1.2           # non-unit on purpose
-    # noised rotation: some close to the prediction (small angles, incl. the small-angle branch), some far
-    q_t = torch.nn.functional.normalize(q_pred + torch.randn(F, N, 4, generator=gen) * torch.logspace(-5, 0.5, N)[None, :, None], dim=-1)
+    # noised rotation at relative angles from ~0.03 rad to pi.  (Below that the reference formula itself is numerically
+    # ill-conditioned in its own fp32 arithmetic — lo*dhi - hi*dlo cancels to (h*omega)^2 of its terms, so3_diffuser.py:
+    # 107-113 — and two correct fp32 evaluations differ by O(1); test_score_epilogue_small_angles covers that range.)
+    q_t = torch.nn.functional.normalize(q_pred + q_pred.norm(dim=-1, keepdim=True) * torch.randn(F, N, 4, generator=gen)
+                                        * torch.logspace(-1.5, 0.5, N)[None, :, None], dim=-1)
     x_pred, x_t = torch.randn(F, N, 3, generator=gen) * 8, torch.randn(F, N, 3, generator=gen)
     mask = (torch.rand(F, N, generator=gen) > 0.2).float()
     t = torch.tensor([tval], dtype=tdtype)
@@ -243,13 +246,32 @@ def test_score_epilogue(tval, tdtype):
     ro, to_, gqo, gxo = run(O.score_epilogue, "cpu")
     rk, tk, gqk, gxk = run(K.score_epilogue, DEV)
     assert rk.dtype == torch.float64 and tk.dtype == to_.dtype
-    assert (ro - rk).norm(dim=-1).max().item() < 1e-4 * max(1.0, ro.norm(dim=-1).max().item())
+    err = ((ro - rk).norm(dim=-1) / ro.norm(dim=-1).clamp(min=1.0)).max().item()
+    assert err < 1e-4, f"rot_score per-residue relative L2 {err:.3e}"
     assert _rel_err(to_.double(), tk.double()) < 2e-6
     assert _rel_err(gxo.double(), gxk.double()) < 2e-6
     assert _rel_err(gqo.double(), gqk.double()) < 2e-4, _rel_err(gqo.double(), gqk.double())
     # rotation score alone (the diffuser API, calc_rot_score)
     r2, none = K.score_epilogue(q_pred.to(DEV), q_t.to(DEV), None, None, t.to(DEV), _grid().to(DEV), None, **kw)
     assert none is None and (r2.cpu() * mask[..., None] - rk).abs().max().item() < 1e-12 * max(1.0, rk.abs().max().item())
+
+
+def test_score_epilogue_small_angles():
+    """Rotation angles down to 1e-6 rad (incl. the small-angle branch of quat_to_rotvec and omega -> eps): finite values
+    and gradients, zero where masked."""
+    n = 64
+    gen = torch.Generator().manual_seed(6)
+    q = torch.nn.functional.normalize(torch.randn(1, n, 4, generator=gen), dim=-1)
+    q_t = torch.nn.functional.normalize(q + torch.randn(1, n, 4, generator=gen) * torch.logspace(-7, -2, n)[None, :, None], dim=-1)
+    q_t[0, 0] = q[0, 0]                                        # exactly equal rotations
+    qp = q.to(DEV).requires_grad_(True)
+    mask = torch.ones(1, n)
+    mask[0, 5] = 0
+    kw = dict(max_sigma=1.5, min_sigma=0.1, min_b=0.1, max_b=20.0, r3_scale=1.0, ipa_scale=1.0, L=1000)
+    rs, _ = K.score_epilogue(qp, q_t.to(DEV), None, None, torch.tensor([0.5]).to(DEV), _grid().to(DEV), mask.to(DEV), **kw)
+    (g,) = torch.autograd.grad(rs.sum(), [qp])
+    assert torch.isfinite(rs).all() and torch.isfinite(g).all()
+    assert float(rs[0, 5].abs().max()) == 0.0 and float(g[0, 5].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("is_mat,want_frames", [(False, False), (True, True), (False, True)])
