@@ -362,7 +362,7 @@ def run_ours(args):
         else (1400.0, "fallback")
     hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     agg = {}
-    for name, work, a, b in prof:
+    for name, work, a, b, _tag in prof:
         t = a.elapsed_time(b) * 1e-3
         d = agg.setdefault(name, [0.0, 0.0, 0])
         d[0] += work

@@ -494,6 +494,102 @@ __global__ void rot_compose_bwd_kernel(const float* __restrict__ Ra, const float
     if (dta) { dta[3 * ia] = gat[0]; dta[3 * ia + 1] = gat[1]; dta[3 * ia + 2] = gat[2]; }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// reverse-diffusion step (f2): one block per trajectory frame.  Replaces src/data/se3_diffuser.py:160-215,
+// so3_diffuser.py:329-365 (geodesic random walk, right multiplication), r3_diffuser.py:106-157 (VP-SDE Euler-Maruyama
+// step + centring) and the scipy rotation-vector round trips (se3_diffuser.py:11-29); the noise is an input.
+// ------------------------------------------------------------------------------------------------------------
+struct ReverseParams {
+    const float* q_t; const float* x_t;          // [F,N,4], [F,N,3]
+    const double* rot_score; const void* trans_score; int trans_is_f64;
+    const float* z_rot; const float* z_trans;    // N(0,1) draws [F,N,3] (already multiplied by noise_scale or not: see noise_scale)
+    const float* mask;                           // diffuse mask [F,N] or null
+    double g_rot, g_trans, b_t, dt, noise_scale, r3_scale;
+    int center, diffuse_rot, diffuse_trans;
+    float* q_out; float* x_out;
+    int N;
+};
+
+__global__ void __launch_bounds__(256) reverse_step_kernel(const ReverseParams p) {
+    __shared__ double s_sum[3][8];
+    __shared__ double s_com[3];
+    const int f = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long base = (long)f * p.N;
+    const double sdt = sqrt(p.dt);
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    // pass 1: translations after the step (scaled units), accumulate the centre of mass
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+        const long r = base + i;
+        if (p.diffuse_trans) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double x = (double)p.x_t[3 * r + c] * p.r3_scale;
+                const double sc = p.trans_is_f64 ? ((const double*)p.trans_score)[3 * r + c] : (double)((const float*)p.trans_score)[3 * r + c];
+                const double z = p.noise_scale * (double)p.z_trans[3 * r + c];
+                const double perturb = (-0.5 * p.b_t * x - p.g_trans * p.g_trans * sc) * p.dt + p.g_trans * sdt * z;
+                const double x1 = x - perturb;
+                (c == 0 ? cx : (c == 1 ? cy : cz)) += x1;
+            }
+        }
+    }
+    if (p.diffuse_trans && p.center) {
+        cx = warp_sum_d(cx); cy = warp_sum_d(cy); cz = warp_sum_d(cz);
+        if (lane == 0) { s_sum[0][wid] = cx; s_sum[1][wid] = cy; s_sum[2][wid] = cz; }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_sum[threadIdx.x][w];
+            s_com[threadIdx.x] = t / (double)p.N;             // r3_diffuser.py:151 with the default all-ones mask
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+        const long r = base + i;
+        const bool upd = p.mask ? (p.mask[r] > 0.5f) : true;    // _apply_mask with a 0/1 mask (se3_diffuser.py:206-210)
+        // ---- translation ----
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float out = p.x_t[3 * r + c];
+            if (p.diffuse_trans && upd) {
+                const double x = (double)p.x_t[3 * r + c] * p.r3_scale;
+                const double sc = p.trans_is_f64 ? ((const double*)p.trans_score)[3 * r + c] : (double)((const float*)p.trans_score)[3 * r + c];
+                const double z = p.noise_scale * (double)p.z_trans[3 * r + c];
+                const double perturb = (-0.5 * p.b_t * x - p.g_trans * p.g_trans * sc) * p.dt + p.g_trans * sdt * z;
+                double x1 = x - perturb;
+                if (p.center) x1 -= s_com[c];
+                out = (float)(x1 / p.r3_scale);
+            }
+            p.x_out[3 * r + c] = out;
+        }
+        // ---- rotation: R_{t-1} = R_t Exp(perturb)  <=>  q_{t-1} = q_t (x) (cos(a/2), sin(a/2) axis) ----
+        const float4 q4 = *reinterpret_cast<const float4*>(p.q_t + 4 * r);
+        double qw = q4.x, qx = q4.y, qy = q4.z, qz = q4.w;
+        const double qn = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+        qw /= qn; qx /= qn; qy /= qn; qz /= qn;
+        if (p.diffuse_rot && upd) {
+            double v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double z = p.noise_scale * (double)p.z_rot[3 * r + c];
+                v[c] = p.g_rot * p.g_rot * p.rot_score[3 * r + c] * p.dt + p.g_rot * sdt * z;
+            }
+            const double a = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            double pw = 1.0, k = 0.5;                       // sin(a/2)/a -> 1/2
+            if (a > 1e-12) { pw = cos(0.5 * a); k = sin(0.5 * a) / a; }
+            const double px = k * v[0], py = k * v[1], pz = k * v[2];
+            const double nw = qw * pw - qx * px - qy * py - qz * pz;
+            const double nx = qw * px + qx * pw + qy * pz - qz * py;
+            const double ny = qw * py - qx * pz + qy * pw + qz * px;
+            const double nz = qw * pz + qx * py - qy * px + qz * pw;
+            const double nn = sqrt(nw * nw + nx * nx + ny * ny + nz * nz);
+            qw = nw / nn; qx = nx / nn; qy = ny / nn; qz = nz / nn;
+        }
+        *reinterpret_cast<float4*>(p.q_out + 4 * r) = make_float4((float)qw, (float)qx, (float)qy, (float)qz);
+    }
+}
+
 int fill_score_params(ScoreParams& p, const float* q_pred, const float* q_t, const float* x_pred, const float* x_t, const double* t,
                       const double* grid, int G, double max_sigma, double min_sigma, double min_b, double max_b, float r3_scale,
                       float ipa_scale, const float* mask, int L, long n) {
@@ -575,4 +671,18 @@ extern "C" int dfold_rot_compose_bwd(const float* rot_a, const float* trans_a, c
     rot_compose_bwd_kernel<<<(unsigned)cdiv(n_a, 128), 128, 0, as_stream(stream)>>>(rot_a, trans_a, rot_b, trans_b, drot_out, dtrans_out,
                                                                                    drot_a, dtrans_a, drot_b, dtrans_b, n_a, rep, inverse);
     return check_launch("rot_compose_bwd_kernel");
+}
+
+extern "C" int dfold_reverse_step(const float* q_t, const float* x_t, const double* rot_score, const void* trans_score, int trans_is_f64,
+                                  const float* z_rot, const float* z_trans, const float* mask, double g_rot, double g_trans, double b_t,
+                                  double dt, double noise_scale, double r3_scale, int center, int diffuse_rot, int diffuse_trans,
+                                  float* q_out, float* x_out, long F, long N, void* stream) {
+    DFOLD_REQUIRE(F > 0 && N > 0, "dfold_reverse_step: empty input");
+    DFOLD_REQUIRE(q_t && x_t && q_out && x_out, "dfold_reverse_step: null frames");
+    DFOLD_REQUIRE(!diffuse_rot || (rot_score && z_rot), "dfold_reverse_step: rotation score / noise missing");
+    DFOLD_REQUIRE(!diffuse_trans || (trans_score && z_trans), "dfold_reverse_step: translation score / noise missing");
+    ReverseParams p{q_t, x_t, rot_score, trans_score, trans_is_f64, z_rot, z_trans, mask, g_rot, g_trans, b_t, dt, noise_scale, r3_scale,
+                    center, diffuse_rot, diffuse_trans, q_out, x_out, (int)N};
+    reverse_step_kernel<<<(unsigned)F, 256, 0, as_stream(stream)>>>(p);
+    return check_launch("reverse_step_kernel");
 }

@@ -191,6 +191,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         f0 = m_tile / p.tiles_per_frame;
         n0 = (m_tile % p.tiles_per_frame) * BM;
         hb = f0 % p.bmod;
+        kb_begin = (int)blockIdx.z * p.kb_per_split;          // split-K over (tap, k-chunk) for launches that cannot fill the chip
+        num_kb = min(p.kb_per_split, p.num_kb - kb_begin);
     } else {
         m0 = m_tile * BM;
         kb_begin = zs * p.kb_per_split;
@@ -226,7 +228,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 const uint32_t sb_hi = sa_lo + Cfg::kABytes;
                 const uint32_t sb_lo = sb_hi + Cfg::kBBytes;
                 if (p.mode == 0) {
-                    const int tap = kb / p.kc, c = kb % p.kc;
+                    const int tap = (kb_begin + kb) / p.kc, c = (kb_begin + kb) % p.kc;
                     const int dn = tap % p.taps_n - p.taps_n / 2;
                     const int df = tap / p.taps_n - p.taps_f / 2;
                     const int ak = c * BK + hb * p.a_k_bstride;
@@ -705,6 +707,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     }
 }
 
+// out = act(out + bias) + beta * res   (second pass of a split-K launch; rows x n_out, row strides ldo / ldr)
+__global__ void gemm_finish_kernel(float* __restrict__ out, long ldo, const float* __restrict__ bias, const float* __restrict__ res,
+                                   long ldr, float beta, int act, long rows, int n_out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * n_out) return;
+    const long r = i / n_out;
+    const int c = (int)(i % n_out);
+    float x = out[r * ldo + c];
+    if (bias) x += __ldg(bias + c);
+    if (act == 1) x = fmaxf(x, 0.f);
+    else if (act == 2) x = x / (1.f + __expf(-x));
+    if (res) x += beta * __ldg(res + r * ldr + c);
+    out[r * ldo + c] = x;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ---------------------------------------------------------------------------------------------------
@@ -867,10 +884,38 @@ extern "C" int dfold_gemm_bf16x3(
         if (pbn == 256) return launch_pair<256>(maps, p, pgrid, st);
         return launch_pair<160>(maps, p, pgrid, st);
     }
-    dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(F_out * p.tiles_per_frame), 1);
-    if (bn == 256) return launch<256>(maps, p, grid, st);
-    if (bn == 128) return launch<128>(maps, p, grid, st);
-    return launch<64>(maps, p, grid, st);
+    // Launches that cannot fill the chip but have a long K loop (the last layers of the dead-frame pyramid: one to a few
+    // frames x 25 taps x C_in) are latency-bound on that loop: split K over blockIdx.z, accumulate with atomics into a
+    // zeroed output, then apply bias / activation / residual in a second pass.
+    const long tiles = cdiv(n_out, bn) * row_tiles;
+    int splits = 1;
+    {
+        const char* off = getenv("DFOLD_GEMM_NO_SPLITK");
+        if (!(off && off[0] == '1') && tiles * 2 <= sm_count() && p.num_kb >= 32 && ldo == n_out) {
+            splits = (int)min((long)16, min(cdiv((long)sm_count(), tiles), (long)p.num_kb / 8));
+            if (splits < 2) splits = 1;
+        }
+    }
+    dim3 grid((unsigned)cdiv(n_out, bn), (unsigned)(F_out * p.tiles_per_frame), (unsigned)splits);
+    if (splits > 1) {
+        p.kb_per_split = (int)cdiv(p.num_kb, splits);
+        grid.z = (unsigned)cdiv(p.num_kb, p.kb_per_split);
+        p.atomic = 1;
+        p.bias = nullptr; p.res = nullptr; p.act = 0; p.beta = 0.f;
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(F_out * Nr) * (size_t)ldo, st);
+        DFOLD_REQUIRE(e == cudaSuccess, "dfold_gemm_bf16x3: memset: %s", cudaGetErrorString(e));
+    }
+    int rc;
+    if (bn == 256) rc = launch<256>(maps, p, grid, st);
+    else if (bn == 128) rc = launch<128>(maps, p, grid, st);
+    else rc = launch<64>(maps, p, grid, st);
+    if (rc || splits == 1) return rc;
+    if (bias || residual || act) {
+        const long total = F_out * Nr * n_out;
+        gemm_finish_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(out, ldo, bias, residual, ldr, beta, act, F_out * Nr, (int)n_out);
+        return check_launch("gemm_finish_kernel");
+    }
+    return 0;
 }
 
 // out[tap][m][n] = alpha * sum_{f, j} A[f][j][m] * B[f + df(tap)][j + dn(tap)][n]      (weight gradient; K = pixels)

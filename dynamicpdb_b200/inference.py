@@ -59,3 +59,53 @@ class MemoizedScoreNetwork(torch.nn.Module):
         out["trans_score"] = diffuser.calc_trans_score(init.get_trans(), pred.get_trans(), t[:, None, None],
                                                        use_torch=True) * node_mask[..., None]
         return out
+
+
+class DeviceReverseDiffusion:
+    """The sampling loop of ``Experiment.inference_fn`` (reference train_DFOLD_dynamics.py:1425-1530) kept on the device:
+
+        one trunk evaluation (memoised: the trunk does not depend on t or on the noised frames)
+        + per reverse step  ONE score-epilogue kernel  +  ONE reverse-step kernel
+
+    instead of ``num_t`` full network evaluations each followed by a numpy / scipy reverse step on the host.
+    BASELINE.json configs[1]: 100 steps, N_res = 256, 32 frames."""
+
+    def __init__(self, net):
+        from .score_epilogue import SE3ScoreDiffuser
+        self.net = net
+        self.memo = MemoizedScoreNetwork(net)
+        sd = getattr(net.score_model, "_fused_scores", None)
+        if not isinstance(sd, SE3ScoreDiffuser):
+            raise ValueError("DeviceReverseDiffusion needs a diffuser with the reference's logarithmic / VP-SDE schedules")
+        self.diffuser = sd
+
+    @torch.no_grad()
+    def sample(self, data_init: Dict[str, torch.Tensor], num_t: int, min_t: float, noise_scale: float = 1.0, center: bool = True,
+               noise=None, generator=None, literal: bool = False):
+        """-> {"prot_traj": [num_t, nf, N, 37, 3] atom37 per step (t = min_t first, as the reference flips it),
+               "rigids": final noised-frame tensor [nf, N, 7], "rigid_pred": [nf, N, 7]}.
+        ``noise``: optional (z_rot, z_trans) pair of [num_t, nf, N, 3] tensors; ``literal=True`` evaluates the whole network
+        at every step as the reference does (for the comparison in tests / bench)."""
+        import numpy as np
+        feats = dict(data_init)
+        dev = feats["rigids_t"].device
+        reverse_steps = np.linspace(min_t, 1.0, num_t)[::-1]
+        dt = 1.0 / num_t
+        model = self.net if literal else self.memo
+        traj = []
+        out = None
+        for i, t in enumerate(reverse_steps):
+            feats["t"] = torch.full((1,), float(t), device=dev, dtype=feats["t"].dtype if "t" in feats else torch.float32)
+            out = model(feats)
+            if t > min_t:
+                diffuse_mask = (1 - feats["fixed_mask"].float()) * feats["res_mask"].float()
+                z = (None, None) if noise is None else (noise[0][i], noise[1][i])
+                rig = self.diffuser.reverse(Rigid.from_tensor_7(feats["rigids_t"].float()), out["rot_score"], out["trans_score"],
+                                            float(t), dt, diffuse_mask=diffuse_mask, center=center, noise_scale=noise_scale,
+                                            z_rot=z[0], z_trans=z[1], generator=generator)
+                feats["rigids_t"] = rig.to_tensor_7()
+            else:
+                feats["rigids_t"] = out["rigids"]
+            feats["sc_ca_t"] = out["rigids"][..., 4:]
+            traj.append(out["atom37"])
+        return {"prot_traj": torch.stack(traj[::-1]), "rigids": feats["rigids_t"], "rigid_pred": out["rigids"]}

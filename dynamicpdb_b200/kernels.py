@@ -53,6 +53,7 @@ _SIGS = {
     "dfold_score_fwd": "ppppp" + "pidddd" + "ffpil" + "ppi" + "p",
     "dfold_score_bwd": "ppppp" + "pidddd" + "ffpil" + "ppi" + "pp" + "p",
     "dfold_frames_to_atoms_fwd": "pippp" + "pppppp" + "ppp" + "lp",
+    "dfold_reverse_step": "ppppi" + "ppp" + "dddddd" + "iii" + "pp" + "llp",
     "dfold_quat_mul_fwd": "ppplip",
     "dfold_quat_mul_bwd": "ppppplip",
     "dfold_rot_compose_fwd": "pppp" + "pp" + "liip",
@@ -102,8 +103,8 @@ def _check(rc: int, what: str):
 class _timed:
     """Brackets one kernel launch with CUDA events on the launching stream when profiling is enabled."""
 
-    def __init__(self, name, work):
-        self.name, self.work = name, work
+    def __init__(self, name, work, tag=""):
+        self.name, self.work, self.tag = name, work, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -115,7 +116,7 @@ class _timed:
     def __exit__(self, *exc):
         if PROFILE is not None and exc[0] is None:
             self.e1.record()
-            PROFILE.append((self.name, self.work, self.e0, self.e1))
+            PROFILE.append((self.name, self.work, self.e0, self.e1, self.tag))
         return False
 
 
@@ -274,7 +275,7 @@ def _conv_planes(w: torch.Tensor):
 def _gemm(a_hi, a_lo, F, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr, alpha, beta, act,
           F_out=None, f_start=0):
     F_out = F if F_out is None else F_out
-    with _timed("gemm_bf16x3", 2.0 * F_out * Nr * K * n_out * taps_f * taps_n):
+    with _timed("gemm_bf16x3", 2.0 * F_out * Nr * K * n_out * taps_f * taps_n, f"kmajor F{F_out} N{Nr} K{K} out{n_out} taps{taps_f * taps_n}"):
         _gemm_launch(a_hi, a_lo, F, F_out, f_start, Nr, K, lda, b_hi, b_lo, n_out, ldb, taps_f, taps_n, out, ldo, bias, residual, ldr,
                      alpha, beta, act)
 
@@ -288,7 +289,7 @@ def _gemm_launch(a_hi, a_lo, F, F_out, f_start, Nr, K, lda, b_hi, b_lo, n_out, l
 
 def _gemm_wgrad(a, M, lda, b, Nn, ldb, F, Nr, taps_f, taps_n, out, ldo, Fb=None, b_f_add=0):
     Fb = F if Fb is None else Fb
-    with _timed("gemm_bf16x3", 2.0 * F * Nr * M * Nn * taps_f * taps_n):
+    with _timed("gemm_bf16x3", 2.0 * F * Nr * M * Nn * taps_f * taps_n, f"wgrad F{F} N{Nr} M{M} n{Nn} taps{taps_f * taps_n}"):
         _gemm_wgrad_launch(a, M, lda, b, Nn, ldb, F, Fb, b_f_add, Nr, taps_f, taps_n, out, ldo)
 
 
@@ -1163,3 +1164,24 @@ class _RotComposeFn(Function):
 def rot_compose(Ra, ta, Rb, tb, inverse: bool = False):
     """Rotation-matrix frames: returns (Ra Rb | None, Ra tb + ta | None); ``inverse``: Ra^T (tb - ta)."""
     return _RotComposeFn.apply(Ra, ta, Rb, tb, inverse)
+
+
+def reverse_step(q_t, x_t, rot_score, trans_score, z_rot, z_trans, mask, *, g_rot, g_trans, b_t, dt, noise_scale=1.0,
+                 r3_scale=1.0, center=True, diffuse_rot=True, diffuse_trans=True):
+    """One reverse-diffusion step of the noised frames on the device (no autograd: sampling runs under no_grad).
+    q_t [F,N,4], x_t [F,N,3], rot_score [F,N,3] fp64, trans_score [F,N,3] fp32/fp64, z_* [F,N,3], mask [F,N] or None."""
+    _need_cuda(q_t, x_t, rot_score, trans_score, z_rot, z_trans, mask)
+    with torch.cuda.device(q_t.device):
+        q_t, x_t, z_rot, z_trans = _f32c(q_t.detach()), _f32c(x_t.detach()), _f32c(z_rot), _f32c(z_trans)
+        rs = rot_score.detach().to(torch.float64).contiguous()
+        ts = trans_score.detach().contiguous()
+        if ts.dtype not in (torch.float32, torch.float64):
+            ts = ts.float()
+        mk = _f32c(mask) if mask is not None else None
+        F_, N_ = q_t.shape[0], q_t.shape[1]
+        q_out, x_out = torch.empty_like(q_t), torch.empty_like(x_t)
+        _check(lib().dfold_reverse_step(_ptr(q_t), _ptr(x_t), _ptr(rs), _ptr(ts), int(ts.dtype == torch.float64), _ptr(z_rot), _ptr(z_trans),
+                                        _ptr(mk), float(g_rot), float(g_trans), float(b_t), float(dt), float(noise_scale), float(r3_scale),
+                                        int(center), int(diffuse_rot), int(diffuse_trans), _ptr(q_out), _ptr(x_out), F_, N_, _stream()),
+               "dfold_reverse_step")
+    return q_out, x_out

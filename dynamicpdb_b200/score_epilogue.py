@@ -66,6 +66,45 @@ class SE3ScoreDiffuser:
         idx = torch.bucketize(s, grid, right=True) - 1
         return grid[idx.clamp(0, grid.numel() - 1)]
 
+    # ---- reverse-diffusion step on the device (se3_diffuser.py:160-215) ----
+    def sigma(self, t: float) -> float:
+        return float(self._sigma_np(np.float64(t)))
+
+    def rot_diffusion_coef(self, t: float) -> float:
+        """so3_diffuser.py:201-210."""
+        s = self.sigma(t)
+        return float(np.sqrt(2 * (np.exp(self.max_sigma) - np.exp(self.min_sigma)) * s / np.exp(s)))
+
+    def b_t(self, t: float) -> float:
+        """r3_diffuser.py:26-29."""
+        return float(self.min_b + t * (self.max_b - self.min_b))
+
+    def reverse(self, rigid_t, rot_score, trans_score, t: float, dt: float, diffuse_mask=None, center: bool = True,
+                noise_scale: float = 1.0, device=None, z_rot=None, z_trans=None, generator=None):
+        """``SE3Diffuser.reverse`` with the reference's signature, executed by ONE kernel on the tensors' device
+        (csrc/epilogue.cu `reverse_step_kernel`): no scipy rotation-vector round trip, no host copies.  Scores / mask may be
+        tensors or numpy arrays (the reference passes numpy).  ``z_rot`` / ``z_trans`` [..,N,3] inject the normal draws
+        (default: drawn on the device from ``generator``; the reference draws from numpy's global stream, so samples agree
+        in distribution, and exactly when the same draws are injected)."""
+        q_t, x_t = rigid_t.get_rots().get_quats(), rigid_t.get_trans()
+        dev = q_t.device
+        as_t = lambda a, dt_=None: (a if torch.is_tensor(a) else torch.as_tensor(np.asarray(a))).to(dev) if a is not None else None
+        rot_score, trans_score, mask = as_t(rot_score), as_t(trans_score), as_t(diffuse_mask)
+        shp = x_t.shape
+        if z_rot is None:
+            z_rot = torch.randn(shp, device=dev, generator=generator)
+        if z_trans is None:
+            z_trans = torch.randn(shp, device=dev, generator=generator)
+        lead = shp[:-2]
+        F_ = int(np.prod(lead)) if len(lead) else 1
+        N_ = shp[-2]
+        v = lambda a, c: a.reshape(F_, N_, c)
+        q1, x1 = K.reverse_step(v(q_t, 4), v(x_t, 3), v(rot_score, 3), v(trans_score, 3), v(as_t(z_rot), 3), v(as_t(z_trans), 3),
+                                None if mask is None else mask.reshape(F_, N_).float(),
+                                g_rot=self.rot_diffusion_coef(t), g_trans=float(np.sqrt(self.b_t(t))), b_t=self.b_t(t), dt=dt,
+                                noise_scale=noise_scale, r3_scale=self.coordinate_scaling, center=center)
+        return ru.Rigid(ru.Rotation(quats=q1.reshape(shp[:-1] + (4,)), normalize_quats=False), x1.reshape(shp))
+
     # ---- se3_diffuser.py:119-125 ----
     def calc_rot_score(self, rots_t, rots_0, t, eps: float = 1e-6):
         q_t, q_0 = rots_t.get_quats(), rots_0.get_quats()

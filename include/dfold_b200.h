@@ -242,6 +242,17 @@ int dfold_rot_compose_bwd(const float* rot_a, const float* trans_a, const float*
                           const float* drot_out, const float* dtrans_out, float* drot_a, float* dtrans_a,
                           float* drot_b, float* dtrans_b, long n_a, int rep, int inverse, void* stream);
 
+/* One reverse-diffusion step t -> t - dt on the device, one block per trajectory frame (src/data/se3_diffuser.py:160-215,
+ * src/data/so3_diffuser.py:329-365, src/data/r3_diffuser.py:106-157; replaces the numpy / scipy round trip of
+ * se3_diffuser.py:11-29).  q_t [F,N,4], x_t [F,N,3] the current noised frames; scores as produced by dfold_score_fwd;
+ * z_rot / z_trans [F,N,3] standard-normal draws (the caller owns the random stream); mask [F,N] 0/1 diffuse mask or NULL;
+ * g_rot = so3 diffusion coefficient g(t), g_trans = sqrt(b(t)), b_t = b(t); centre-of-mass removal over each frame.
+ * Writes unit quaternions q_out [F,N,4] (q_t (x) Exp(perturbation), right multiplication) and x_out [F,N,3]. */
+int dfold_reverse_step(const float* q_t, const float* x_t, const double* rot_score, const void* trans_score, int trans_is_f64,
+                       const float* z_rot, const float* z_trans, const float* mask, double g_rot, double g_trans, double b_t,
+                       double dt, double noise_scale, double r3_scale, int center, int diffuse_rot, int diffuse_trans,
+                       float* q_out, float* x_out, long F, long N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

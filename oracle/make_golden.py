@@ -85,6 +85,34 @@ def run_net_big(name="net_A256", nf=64, N=256, seed=7):
     print(name, "loss", float(syn.surrogate_loss(out)))
 
 
+def reverse_case():
+    """Inputs of the reverse-step fixture (shared with the tests): noised frames, scores, mask; the normal draws come from
+    numpy's legacy global stream seeded with 77 — so3 first, then r3, as SE3Diffuser.reverse consumes them."""
+    import numpy as np
+    F, N = 3, 11
+    g = torch.Generator().manual_seed(71)
+    rig = syn.make_feats(F, N, seed=9)["rigids_t"]
+    rig = torch.cat([rig[..., :4], rig[..., 4:] * 6.0], dim=-1)
+    rot_score = torch.randn(F, N, 3, generator=g, dtype=torch.float64) * 0.8
+    trans_score = torch.randn(F, N, 3, generator=g, dtype=torch.float64) * 0.5
+    mask = (torch.rand(F, N, generator=g) > 0.25).double()
+    return dict(rig=rig, rot_score=rot_score, trans_score=trans_score, mask=mask, t=0.37, dt=0.01, noise_scale=0.7, cs=0.1, seed=77)
+
+
+def run_reverse():
+    """SE3Diffuser.reverse of the unmodified reference (se3_diffuser.py:160-215)."""
+    import numpy as np
+    c = reverse_case()
+    diff = se3_diffuser.SE3Diffuser(syn.diffuser_conf(c["cs"]))
+    np.random.seed(c["seed"])
+    out = diff.reverse(rigid_t=RefRU.Rigid.from_tensor_7(c["rig"]), rot_score=c["rot_score"].numpy(), trans_score=c["trans_score"].numpy(),
+                       diffuse_mask=c["mask"].numpy(), t=c["t"], dt=c["dt"], center=True, noise_scale=c["noise_scale"])
+    t7 = out.to_tensor_7()
+    t7 = torch.cat([torch.where(t7[..., :1] < 0, -t7[..., :4], t7[..., :4]), t7[..., 4:]], dim=-1)     # eigh sign is arbitrary
+    torch.save({"rigids_t_1": t7.float()}, os.path.join(OUT, "reverse.pt"))
+    print("reverse ok")
+
+
 def run_vanilla():
     torch.manual_seed(0)
     c_s, c_z, c_h, H, Pq, Pv, N, B = 32, 16, 8, 4, 4, 8, 14, 2
@@ -174,6 +202,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         run_net_big()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "reverse":
+        run_reverse()
+        sys.exit(0)
+    run_reverse()
     run_transitions()
     for n, c in NET_CASES.items():
         run_net(n, c)

@@ -124,6 +124,19 @@ def frames_to_atoms(rot, trans, alpha, aatype, tables, eager, want_frames=False,
     return (a14, a37, fr) if want_frames else (a14, a37)
 
 
+def reverse_step(q_t, x_t, rot_score, trans_score, z_rot, z_trans, mask, *, g_rot, g_trans, b_t, dt, noise_scale=1.0,
+                 r3_scale=1.0, center=True, diffuse_rot=True, diffuse_trans=True):
+    """One reverse-diffusion step through the oracle's scipy statement (the schedule constants are re-derived from t there,
+    so this seam recovers t from b_t = min_b + t (max_b - min_b) of the default schedule)."""
+    dc = O.default_diffuser_conf(r3_scale)
+    t = (b_t - dc.min_b) / (dc.max_b - dc.min_b)
+    assert diffuse_rot and diffuse_trans
+    out = O.reverse_step(torch.cat([q_t, x_t], dim=-1).cpu(), rot_score.cpu().numpy(), trans_score.cpu().numpy(), float(t), float(dt),
+                         None if mask is None else mask.cpu().numpy(), z_rot.cpu().numpy(), z_trans.cpu().numpy(), dc,
+                         center=center, noise_scale=noise_scale).to(q_t.device)
+    return out[..., :4], out[..., 4:]
+
+
 def quat_mul(a, b, b_is_vec=False):
     if b_is_vec:
         b = torch.cat([torch.zeros_like(b[..., :1]), b], dim=-1)
@@ -144,5 +157,5 @@ def rot_compose(Ra, ta, Rb, tb, inverse=False):
     return Ro, to
 
 
-ALL = ["score_epilogue", "frames_to_atoms", "quat_mul", "rot_compose", "linear", "conv5x5", "global_layernorm", "layer_norm", "quat_to_rot", "rigid_apply", "ipa_points",
+ALL = ["score_epilogue", "frames_to_atoms", "reverse_step", "quat_mul", "rot_compose", "linear", "conv5x5", "global_layernorm", "layer_norm", "quat_to_rot", "rigid_apply", "ipa_points",
        "compose_q_update", "keep_last_frame", "qk_logits", "ipa_attention"]

@@ -46,7 +46,7 @@ def run_bwd(F, N, Ci, Co, reps=3):
         torch.autograd.grad(y, [x, w, b], g, retain_graph=True)
     torch.cuda.synchronize()
     prof, K.PROFILE = K.PROFILE, None
-    ts = [a.elapsed_time(bb) for (_, _, a, bb) in prof][2:]
+    ts = [a.elapsed_time(bb) for (_, _, a, bb, _t) in prof][2:]
     dg, wg = ts[0::2], ts[1::2]
     fl = 2.0 * F * N * 25 * Ci * Co
     print(f"conv bwd {F}x{N} {Ci}->{Co}: dgrad {sum(dg)/len(dg):.3f} ms ({fl/(sum(dg)/len(dg))/1e9:.0f} TF)  "
