@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-literal", action="store_true", help="skip the extra measurement with dead-frame elimination off")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames in the bounded CPU sample")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs (100-step inference, N_res=1024)")
     return ap.parse_args()
 
 
@@ -246,6 +247,115 @@ def _log(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')} t={time.perf_counter():.1f}] {msg}", file=sys.stderr, flush=True)
 
 
+
+def time_ipa_core(dev, nf, N, iters=20):
+    """Fused IPA forward core alone at the benchmark shape (preset A), CUDA events on the launching stream around `iters`
+    back-to-back calls after 3 warm-up calls.  Inputs (q/k/v, points, pair, bias: 659 MB at nf=64) exceed the 126 MB L2."""
+    from dynamicpdb_b200 import kernels as K
+    H, C, Pq, Pv, Cp = 8, 256, 8, 12, 32
+    g = torch.Generator(device=dev).manual_seed(0)
+    R = lambda *s, scale=1.0: torch.randn(*s, device=dev, generator=g) * scale
+    logit0, kv = R(1, H, N, N), R(1, N, H, 2 * C)
+    q_pts, kv_pts = R(nf, N, H, Pq, 3, scale=4.0), R(nf, N, H, Pq + Pv, 3, scale=4.0)
+    pair = R(1, N, N, Cp)
+    quat = torch.nn.functional.normalize(R(nf, N, 4), dim=-1)
+    trans, mask = R(nf, N, 3, scale=8.0), torch.ones(nf, N, device=dev)
+    gamma = torch.rand(H, device=dev, generator=g) * 0.2 + 0.05
+    alg = 4.0 * (nf * N * (H * (4 * C + 3 * (2 * Pq + Pv) + 8 * Pv + Cp) + 8) + N * N * (H + Cp))
+
+    def run():
+        with torch.no_grad():
+            return K.ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq=Pq, Pv=Pv, dfold=True,
+                                   inf=1e5, eps=1e-8)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    K.LAUNCH_COUNT = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, alg, K.LAUNCH_COUNT // iters
+
+
+def _fresh_net(nf, dev):
+    from dynamicpdb_b200 import synthetic as syn
+    from dynamicpdb_b200.Dfold_network_dynamic import FullScoreNetwork
+    from dynamicpdb_b200.score_epilogue import SE3ScoreDiffuser
+    torch.manual_seed(0)
+    net = FullScoreNetwork(syn.model_conf(nf, **syn.PRESET_A), SE3ScoreDiffuser(syn.diffuser_conf(1.0)))
+    sd = net.state_dict()
+    syn.dezero_(sd)
+    net.load_state_dict(sd)
+    return net.to(dev)
+
+
+def extra_configs(dev, graph):
+    """BASELINE.json configs[1] (100-step reverse diffusion, N_res=256, 32 frames) and configs[4] (N_res=1024, 8 frames,
+    fwd+bwd+Adam) on one GPU.  Secondary lines: wall time of whole jobs, CUDA events, inputs resident."""
+    from dynamicpdb_b200 import synthetic as syn
+    from dynamicpdb_b200.inference import DeviceReverseDiffusion
+    from dynamicpdb_b200.train_step import TrainStep
+    out = {}
+    try:
+        nf, N, num_t = 32, 256, 100
+        net = _fresh_net(nf, dev).eval()
+        feats = {k: v.to(dev) for k, v in syn.make_feats(nf, N, seed=1).items()}
+        gen = torch.Generator(device=dev).manual_seed(0)
+        sampler = DeviceReverseDiffusion(net)
+        res = {}
+        for name, literal, reps in (("memoised", False, 3), ("literal", True, 1)):
+            sampler.memo.reset()
+            sampler.sample(feats, 3, 0.01, generator=gen, literal=literal)        # warm-up
+            sampler.memo.reset()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                sampler.memo.reset()
+                sampler.sample(feats, num_t, 0.01, generator=gen, literal=literal)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            res[name] = {"ms_per_sample": ms, "frames_per_s": nf / (ms * 1e-3), "denoise_steps_per_s": num_t / (ms * 1e-3)}
+        out["inference_100step"] = {
+            "workload": "configs[1]: 100-step reverse diffusion, N_res=256, 32 frames, 1 GPU", **res,
+            "note": "memoised = one trunk pass + 100 x (score-epilogue kernel + reverse-step kernel) on the device; literal = the "
+                    "reference's schedule (whole network at every step) with the device reverse step"}
+        del net, sampler, feats
+        torch.cuda.empty_cache()
+    except Exception as e:      # noqa: BLE001
+        out["inference_100step"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    try:
+        nf, N = 8, 1024
+        net = _fresh_net(nf, dev)
+        feats = {k: v.to(dev) for k, v in syn.make_feats(nf, N, seed=2).items()}
+        ts = TrainStep(net, syn.surrogate_loss, feats, lr=1e-4, world_size=1, graph=graph, warmup=2)
+        for _ in range(2):
+            ts()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 5
+        e0.record()
+        for _ in range(n):
+            ts()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        ipa_ms, alg, _ = time_ipa_core(dev, nf, N, iters=5)
+        out["long_chain_1024"] = {
+            "workload": "configs[4]: training step fwd+bwd+Adam, N_res=1024, 8 frames, 1 GPU", "ms_per_step": ms,
+            "frames_per_s": nf / (ms * 1e-3), "cuda_graph": ts.graph is not None,
+            "ipa_core_fwd": {"ms": ipa_ms, "algorithmic_GBs": alg / ipa_ms / 1e6, "algorithmic_MB": alg / 1e6}}
+        del net, ts, feats
+        torch.cuda.empty_cache()
+    except Exception as e:      # noqa: BLE001
+        out["long_chain_1024"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from dynamicpdb_b200 import kernels as K
@@ -284,7 +394,8 @@ def run_ours(args):
     ts = TrainStep(net, syn.surrogate_loss, resident, lr=1e-4, world_size=world, graph=not args.no_graph,
                    warmup=max(3, args.warmup))
 
-    _log(f"train step ready (graph={ts.graph is not None}, err={ts.graph_error})")
+    graph_on, graph_err = ts.graph is not None, ts.graph_error
+    _log(f"train step ready (graph={graph_on}, err={graph_err})")
 
     def barrier():
         if world > 1:
@@ -361,6 +472,11 @@ def run_ours(args):
     tf_peak, tf_src = (peaks.get("bf16_tflops_sustained"), "measured (sustained)") if peaks.get("bf16_tflops_sustained") \
         else (1400.0, "fallback")
     hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
     agg = {}
     for name, work, a, b, _tag in prof:
         t = a.elapsed_time(b) * 1e-3
@@ -374,18 +490,31 @@ def run_ours(args):
         ach = w / t / 1e12
         roof = {"kernel": "gemm_bf16x3_kernel (implicit 5x5 conv / linear, 3 bf16 MMAs per fp32 product)",
                 "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                "peak_source": tf_src, "traffic": None, "launches_timed": n, "avg_launch_ms": 1e3 * t / n,
+                "peak_source": tf_src, "traffic": traffic.get("gemm_dram_bytes_per_launch"),
+                "traffic_note": traffic.get("gemm_note"), "launches_timed": n, "avg_launch_ms": 1e3 * t / n,
                 "share_of_step": (t / prof_steps) / (ms * 1e-3), "tensor_pipe_frac": 3 * ach / tf_peak,
                 "timed_in": "eager instrumented steps right after the timed (graph-replayed) region",
                 "note": "achieved counts fp32-equivalent FLOPs; the split issues 3 bf16 MMAs per product, so frac <= 1/3"}
     roof_ipa = None
-    if "ipa_fwd" in agg:
-        w, t, n = agg["ipa_fwd"]
-        ach = w / t / 1e9
-        roof_ipa = {"kernel": "ipa_fwd_kernel (fused IPA core)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src, "traffic": None,
-                    "launches_timed": n, "avg_launch_ms": 1e3 * t / n, "share_of_step": (t / prof_steps) / (ms * 1e-3),
-                    "note": "prob kernel + tcgen05 P.V + pair kernel; algorithmic bytes per SURVEY.md 8(d) (per-frame q/k/v formulation)"}
+    try:
+        ipa_ms, ipa_alg, ipa_launches = time_ipa_core(dev, nf, N)
+        ach = ipa_alg / ipa_ms / 1e6
+        in_step = None
+        if "ipa_fwd" in agg:
+            w, t, n = agg["ipa_fwd"]
+            in_step = {"launches_timed": n, "avg_ms_eager_events": 1e3 * t / n,
+                       "note": "event pairs around the op inside the eager instrumented steps; includes host launch gaps"}
+        roof_ipa = {"kernel": "ipa_fused_fwd_kernel + tcgen05 P.V (fused IPA forward core, SURVEY.md 8d)", "bound": "hbm",
+                    "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
+                    "traffic": traffic.get("ipa_fwd_dram_bytes_per_launch"), "algorithmic_bytes": ipa_alg,
+                    "avg_launch_ms": ipa_ms, "kernels_per_call": ipa_launches, "calls_per_step": 4,
+                    "share_of_step": 4 * ipa_ms / ms, "in_step": in_step,
+                    "timed_in": "20 back-to-back calls of the op at the benchmark shape, CUDA events on the launching stream, "
+                                "inputs (659 MB) larger than L2",
+                    "note": "algorithmic bytes per SURVEY.md 8(d) (per-frame q/k/v formulation); the training forward also "
+                            "writes the bf16 probability planes (134 MB) the backward GEMMs read"}
+    except Exception as e:      # noqa: BLE001
+        roof_ipa = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -394,6 +523,13 @@ def run_ours(args):
                "sample": f"{r['steps_timed']} fwd+bwd of {args.cpu_frames} frames x {N} residues ({r['ms'] / 1e3:.1f} s each, "
                          f"after {r['warmup_run']} warm-up), {r['what']}", "thread_info": r["thread_info"]}
 
+    extra = None
+    if world == 1 and not args.no_extra:
+        del ts
+        torch.cuda.empty_cache()
+        extra = extra_configs(dev, not args.no_graph)
+        ts = None
+
     line = {
         "metric": METRIC, "value": world * nf / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -401,12 +537,12 @@ def run_ours(args):
         "config": {"workload": f"DFOLDv2 training step fwd+bwd+Adam, N_res={N}, batch={nf} frames per rank (configs[2])",
                    "frames_per_rank": nf, "n_res": N, "preset": "train_DFOLDv2.yaml (c_s 256, c_z 128, C 256, H 8, Pq 8, Pv 12, 4 blocks)",
                    "parallelism": f"dp{world}", "l2": "working set (weights 738 MB + activations) exceeds the 126 MB L2",
-                   "cuda_graph": ts.graph is not None, "cuda_graph_error": ts.graph_error,
+                   "cuda_graph": graph_on, "cuda_graph_error": graph_err,
                    "dead_frame_elimination": os.environ.get("DFOLD_NO_DEAD_FRAME_SKIP", "0") != "1"},
         "e2e": {"value": world * nf / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_ipa": roof_ipa, "cpu_baseline": cpu,
-        "literal_schedule": literal,
+        "literal_schedule": literal, "extra_configs": extra,
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     _finish(world, dist)

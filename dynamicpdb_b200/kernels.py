@@ -47,6 +47,7 @@ _SIGS = {
     "dfold_ipa_pre_bwd": "pp" + "iiiiiii" + "pp" + "pppp" + "p",
     "dfold_ipa_prob_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
     "dfold_ipa_pair_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
+    "dfold_ipa_fused_fwd": "pppppppp" + "ppl" + "ppl" + "iiiiiiii" + "ff" + "pp",
     "dfold_ipa_ds_bwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "ppppp" + "pppp" + "p",
     "dfold_gemm_bf16x3_batched": "ppllll" + "liill" + "ppllll" + "llil" + "pllilf" + "p",
     "dfold_gemm_wgrad_bf16x3_batched": "pplllll" + "pplllll" + "lll" + "ii" + "iiiil" + "pllf" + "p",
@@ -841,20 +842,39 @@ class _IpaAttnTCFn(Function):
         dev = q_pts.device
         n8 = _pad8(N_)
         cat = torch.empty((F_, N_, D), dtype=torch.float32, device=dev)
-        p_hi = torch.empty((F_, H_, N_, n8), dtype=torch.int16, device=dev)
-        p_lo = torch.empty((F_, H_, N_, n8), dtype=torch.int16, device=dev)
+        fused = _fused_fwd_ok(H_, Pq, Pv, Cp)
+        fused_tc = fused and C_ == 256 and os.environ.get("DFOLD_IPA_FUSED_TC", "1") != "0"
+        # the probability planes feed the backward GEMMs (and the separate P V GEMM when the forward is not fully fused)
+        need_planes = (not fused_tc) or any(ctx.needs_input_grad)
+        p_hi = torch.empty((F_, H_, N_, n8), dtype=torch.int16, device=dev) if need_planes else None
+        p_lo = torch.empty((F_, H_, N_, n8), dtype=torch.int16, device=dev) if need_planes else None
         args = _IpaAttnTCFn._v2args(logit0, q_pts, kv_pts, pair, quat, trans, mask, gamma, p_hi, p_lo, n8, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
         alg_bytes = 4.0 * (F_ * N_ * (H_ * (4 * C_ + 3 * (2 * Pq + Pv) + 8 * Pv + Cp) + 8) + N_ * N_ * (H_ + Cp))
+        kv_hi = kv_lo = None
         with _timed("ipa_fwd", alg_bytes):
-            _check(lib().dfold_ipa_prob_fwd(*args, _ptr(cat), _stream()), "dfold_ipa_prob_fwd")
-            # O = P V  on the tensor cores, written into the o-columns of the concat buffer
-            vt = kv[0, :, :, C_:].permute(1, 2, 0).reshape(H_ * C_, N_).contiguous()        # [H*C, N]
-            vt_hi, vt_lo = _planes_rows(vt)
-            _check(lib().dfold_gemm_bf16x3_batched(
-                _ptr(p_hi), _ptr(p_lo), F_ * H_, N_, N_, n8, F_ * H_, H_, 1, 0, N_,
-                _ptr(vt_hi), _ptr(vt_lo), H_, C_, N_, vt_hi.shape[1], 0, 0, 1, C_,
-                _ptr(cat), D, F_ * N_, H_, C_, 1.0, _stream()), "dfold_gemm_bf16x3_batched")
-            _check(lib().dfold_ipa_pair_fwd(*args, _ptr(cat), _stream()), "dfold_ipa_pair_fwd")
+            if fused:
+                # one kernel: distances, exact softmax, pair + value-point aggregation, frame transform, P planes and
+                # (fused_tc) O = P V on tcgen05 straight from the shared-memory P tile
+                if fused_tc:
+                    kv_hi, kv_lo = _planes_rows(kv.reshape(N_, H_ * 2 * C_))                # [N, H*2C] bf16 hi / lo
+                _check(lib().dfold_ipa_fused_fwd(_ptr(logit0), _ptr(q_pts), _ptr(kv_pts), _ptr(pair), _ptr(quat), _ptr(trans),
+                                                 _ptr(mask), _ptr(gamma), _ptr(p_hi), _ptr(p_lo), n8,
+                                                 _ptr(kv_hi), _ptr(kv_lo), 0 if kv_hi is None else kv_hi.shape[1],
+                                                 F_, N_, H_, C_, Pq, Pv, Cp, int(dfold), inf, eps, _ptr(cat), _stream()),
+                       "dfold_ipa_fused_fwd")
+            else:
+                _check(lib().dfold_ipa_prob_fwd(*args, _ptr(cat), _stream()), "dfold_ipa_prob_fwd")
+            if not fused_tc:
+                # O = P V  on the tensor cores, written into the o-columns of the concat buffer
+                vt = kv[0, :, :, C_:].permute(1, 2, 0).reshape(H_ * C_, N_).contiguous()        # [H*C, N]
+                vt_hi, vt_lo = _planes_rows(vt)
+                _check(lib().dfold_gemm_bf16x3_batched(
+                    _ptr(p_hi), _ptr(p_lo), F_ * H_, N_, N_, n8, F_ * H_, H_, 1, 0, N_,
+                    _ptr(vt_hi), _ptr(vt_lo), H_, C_, N_, vt_hi.shape[1], 0, 0, 1, C_,
+                    _ptr(cat), D, F_ * N_, H_, C_, 1.0, _stream()), "dfold_gemm_bf16x3_batched")
+            if not fused:
+                _check(lib().dfold_ipa_pair_fwd(*args, _ptr(cat), _stream()), "dfold_ipa_pair_fwd")
+        ctx.kv_planes = (kv_hi, kv_lo)
         ctx.save_for_backward(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, cat, p_hi, p_lo)
         ctx.meta = (Pq, Pv, dfold, inf, eps)
         return cat
@@ -880,7 +900,9 @@ class _IpaAttnTCFn(Function):
                                        _ptr(d_og), _ptr(delta), _ptr(dquat), _ptr(dtrans), _stream()), "dfold_ipa_pre_bwd")
         # ---- dP = dO V^T  (batched over (f, h); K = the head's C columns of dO) ----
         dc_hi, dc_lo = _planes_rows(dcat.reshape(F_ * N_, D))                       # [F*N, D8]
-        kv_hi, kv_lo = _planes_rows(kv.reshape(N_, H_ * 2 * C_))                    # [N, H*2C]
+        kv_hi, kv_lo = ctx.kv_planes
+        if kv_hi is None:
+            kv_hi, kv_lo = _planes_rows(kv.reshape(N_, H_ * 2 * C_))                # [N, H*2C]
         dP = new(F_, H_, N_, N_)
         _check(lib().dfold_gemm_bf16x3_batched(
             _ptr(dc_hi), _ptr(dc_lo), F_, N_, D, dc_hi.shape[1], F_ * H_, H_, H_, C_, C_,
@@ -932,6 +954,11 @@ class _IpaAttnTCFn(Function):
             _ptr(dpair), Cp, N_ * Cp, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3_batched")
         dlogit0 = dS.sum(0, keepdim=True) if logit0.shape[0] == 1 else dS
         return dlogit0, dkv, dq_pts, dkv_pts, dpair, dquat, dtrans, None, dgamma, None, None, None, None, None
+
+
+def _fused_fwd_ok(H, Pq, Pv, Cp) -> bool:
+    """csrc/ipa_fused.cu is built for the DFOLDv2 preset-A head geometry; DFOLD_IPA_UNFUSED=1 keeps the three-kernel path."""
+    return H == 8 and Pq == 8 and Pv == 12 and Cp == 32 and os.environ.get("DFOLD_IPA_UNFUSED", "0") != "1"
 
 
 def _tc_path_ok(logit0, kv, q_pts, pair, Pq, Pv) -> bool:

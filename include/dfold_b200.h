@@ -184,6 +184,17 @@ int dfold_ipa_pair_fwd(const float* logit0, long logit0_fstride, const float* q_
                        long pair_fstride, const float* quat, const float* trans, const float* mask, const float* gamma,
                        uint16_t* p_hi, uint16_t* p_lo, long ldp, int F, int N, int H, int C, int Pq, int Pv, int Cp,
                        int dfold, float inf, float eps, float* out_cat, void* stream);
+/* Fused forward core (csrc/ipa_fused.cu), frame-shared logit0 [H,N,N] and pair [N,N,Cp]: one kernel does the point
+ * distances (exact fp32), the exact two-pass softmax, the pair and value-point aggregations, the local-frame transform and
+ * the concat layout; p_hi / p_lo (nullable: inference) receive the bf16 hi/lo probability planes for the backward GEMMs.
+ * kv_hi / kv_lo: bf16 hi/lo planes of kv [N, H*2C] (row stride ldkv); when given (C = 256) the scalar values o = P V are
+ * produced in the same kernel by tcgen05.mma from a shared-memory P tile into TMEM (P does not travel through HBM);
+ * when null, columns [0, H*C) of the concat buffer are left to dfold_gemm_bf16x3_batched.  H=8, Pq=8, Pv=12, Cp=32.
+ * Replaces src/model/ipa_pytorch_dynamic.py:402-504. */
+int dfold_ipa_fused_fwd(const float* logit0, const float* q_pts, const float* kv_pts, const float* pair, const float* quat,
+                        const float* trans, const float* mask, const float* gamma, uint16_t* p_hi, uint16_t* p_lo, long ldp,
+                        const uint16_t* kv_hi, const uint16_t* kv_lo, long ldkv, int F, int N, int H, int C, int Pq, int Pv,
+                        int Cp, int dfold, float inf, float eps, float* out_cat, void* stream);
 /* Epilogue backward: d_og [F,N,H,Pv,3], delta [F,H,N], dquat [F,N,4], dtrans [F,N,3]. */
 int dfold_ipa_pre_bwd(const float* quat, const float* trans, int F, int N, int H, int C, int Pv, int Cp, int dfold,
                       const float* out_cat, const float* dcat, float* d_og, float* delta, float* dquat, float* dtrans,
