@@ -78,6 +78,7 @@ struct GemmParams {
     int atomic;             // epilogue accumulates with atomicAdd (split-K)
     int shift_on_a;         // pair kernel, mode 1: the tap shift / frame offset applies to operand A (roles swapped)
     long o_rs, o_cs;        // pair kernel, mode 1: output element (row m, column n) at out[m * o_rs + n * o_cs]
+    int raster_n;           // pair kernel, mode 0: column tiles fastest in the dispatch order
     long long* stats;       // debug (dfold_debug_gemm_stats): per CTA {total, MMA wait full, MMA wait acc_empty, acc warp wait} cycles
 };
 
@@ -488,8 +489,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const bool leader = rank == 0;
 
     // ---- tile coordinates: the pair owns row tiles 2j, 2j+1 and one BN-wide column tile ----
-    const int m_tile = blockIdx.x;
-    const int n_tile = blockIdx.y;
+    // Raster order: the hardware dispatches CTAs x-fastest.  With `raster_n` the linear pair index runs over the column
+    // tiles first, so the pairs in flight share a narrow band of activation rows and the whole weight tensor (both L2
+    // resident) instead of streaming the entire activation once per column tile.
+    int m_tile = blockIdx.x;
+    int n_tile = blockIdx.y;
+    if (p.raster_n) {
+        const int lin = (int)blockIdx.y * ((int)gridDim.x >> 1) + ((int)blockIdx.x >> 1);
+        n_tile = lin % (int)gridDim.y;
+        m_tile = 2 * (lin / (int)gridDim.y) + ((int)blockIdx.x & 1);
+    }
     const int zq = blockIdx.z;                                 // mode 1: tap
     const int f0 = m_tile / p.tiles_per_frame;                 // mode 0; beyond the last frame for a padding CTA: loads zero-fill
     const int n0 = (m_tile % p.tiles_per_frame) * BM;
@@ -881,6 +890,14 @@ extern "C" int dfold_gemm_bf16x3(
     cudaStream_t st = as_stream(stream);
     if (pbn) {
         dim3 pgrid((unsigned)(2 * cdiv(row_tiles, 2)), (unsigned)cdiv(n_out, pbn), 1);
+        {
+            // activation planes (hi + lo) that fit in L2 next to a weight slice: rows fastest (each column sweep re-reads them
+            // from L2); larger than that: columns fastest (measured, ncu dram bytes: 1280->640 conv 772 -> 408 MB per launch,
+            // 640->1280 conv 173 MB rows-fastest vs 608 MB columns-fastest)
+            const char* e = getenv("DFOLD_GEMM_RASTER");
+            const double a_bytes = 4.0 * (double)F * (double)Nr * (double)lda;
+            p.raster_n = e ? (e[0] == 'n') : (a_bytes > 64e6);
+        }
         if (pbn == 256) return launch_pair<256>(maps, p, pgrid, st);
         return launch_pair<160>(maps, p, pgrid, st);
     }

@@ -55,6 +55,7 @@ struct FusedParams {
     float* cat;                            // [F,N,D]
     int F, N, C, dfold;
     float inf, eps;
+    long long* stats;                      // development aid (dfold_debug_ipa_stats): 16 x int64 cycle counters per CTA
     int skip;                              // development knob (DFOLD_IPA_DEBUG_SKIP): bit 0 pass 1, 1 distances, 2 B1, 3 B2, 4 MMA
 };
 
@@ -271,16 +272,21 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
                 tma_load_3d(dst + 8192, &map_v_lo, full_bar(s), c0, t * FTJ, 0);
                 tma_load_3d(dst + 12288, &map_v_lo, full_bar(s), c0 + 64, t * FTJ, 0);
             };
+            long long w_full = 0, w_ready = 0, w_empty = 0, t_begin = p.stats ? clock64() : 0;
             for (int g = 0; g < min(kRingStages - 1, G); ++g) issue(g);
             for (int g = 0; g < G; ++g) {
                 const int s = g % kRingStages;
                 const int t = g / (2 * FH), rem = g % (2 * FH), hh = rem >> 1, mh = rem & 1;
                 const int par = t & 1;
                 if (rem == 0) {
+                    const long long t0 = p.stats ? clock64() : 0;
                     mbar_wait(pready_bar(par), (t >> 1) & 1);           // phase A of tile t has written its P^T half
+                    if (p.stats) w_ready += clock64() - t0;
                     tcgen05_fence_after();
                 }
+                const long long t1 = p.stats ? clock64() : 0;
                 mbar_wait(full_bar(s), (g / kRingStages) & 1);
+                if (p.stats) w_full += clock64() - t1;
                 tcgen05_fence_after();
                 const uint32_t sa = ring_u32 + s * kRingStage;
                 const uint64_t da_hi = make_sw128_mn_desc(sa, 4096), da_lo = make_sw128_mn_desc(sa + 8192, 4096);
@@ -300,7 +306,15 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
                     umma_commit(pfree_bar(par));                          // this P^T half may be overwritten (tile t + 2)
                     if (t == ntiles - 1) umma_commit(accdone_bar);
                 }
-                if (g + kRingStages - 1 < G) issue(g + kRingStages - 1);
+                if (g + kRingStages - 1 < G) {
+                    const long long t2 = p.stats ? clock64() : 0;
+                    issue(g + kRingStages - 1);
+                    if (p.stats) w_empty += clock64() - t2;
+                }
+            }
+            if (p.stats) {
+                long long* st = p.stats + 16 * ((long)blockIdx.y * gridDim.x + blockIdx.x);
+                st[0] = clock64() - t_begin; st[1] = w_full; st[2] = w_ready; st[3] = w_empty;
             }
         }
     } else {
@@ -333,6 +347,8 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
         const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(s_q + (h * FTI + rbase) * PQ3);
         const float2* rowc = reinterpret_cast<const float2*>(s_row) + rbase;
         comp_sync();
+        const bool timing = p.stats != nullptr && tid == 0;
+        long long tc0 = timing ? clock64() : 0, c_p1 = 0, c_a = 0, c_b1 = 0, c_b2 = 0, c_sync = 0, c_epi = 0;
 
         // =============================== pass 1: softmax statistics ===============================
         // key tiles arrive by TMA (8 boxes of 24 coordinates x 32 residues, one per head), double-buffered in the s_v / s_p
@@ -388,6 +404,7 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
             }
         }
         comp_sync();
+        if (timing) { c_p1 = clock64() - tc0; }
 
         // =============================== pass 2: probabilities and aggregations ===============================
         u64 accp[2][4];                      // pair aggregation: [row of this warp][head pair] x this lane's channel
@@ -423,6 +440,7 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
                 __syncwarp();
             }
             // ---- phase A: warp = (head, row half), lane = key ----
+            long long tt = timing ? clock64() : 0;
             {
                 const int j = j0 + lane;
                 const bool jok = j < N;
@@ -472,7 +490,9 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
                 }
             }
             if (TC) fence_proxy_async();                              // generic-proxy stores of P^T -> visible to the tensor core
+            if (timing) { const long long n = clock64(); c_a += n - tt; tt = n; }
             comp_sync();
+            if (timing) { const long long n = clock64(); c_sync += n - tt; tt = n; }
             if (TC && tid == 0) mbar_arrive(pready_bar(par));
             // ---- phase B1: pair aggregation, warp = 2 rows, lane = pair channel ----
             if (!(p.skip & 4)) {
@@ -507,6 +527,7 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
                     }
                 }
             }
+            if (timing) { const long long n = clock64(); c_b1 += n - tt; tt = n; }
             // ---- phase B2: value points, warp = (head, coordinates 0..19 | 20..35), lane = row ----
             mbar_wait(vfull_bar, t & 1);
             if (!(p.skip & 8)) {
@@ -543,8 +564,11 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
                     }
                 }
             }
+            if (timing) { const long long n = clock64(); c_b2 += n - tt; tt = n; }
             comp_sync();
+            if (timing) { const long long n = clock64(); c_sync += n - tt; tt = n; }
         }
+        const long long te0 = timing ? clock64() : 0;
 
         // =============================== epilogue ===============================
         const int D = FH * (p.C + (p.dfold ? 8 : 4) * FPV + FCP);
@@ -635,6 +659,11 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
                 *reinterpret_cast<float4*>(dst) = v;
             }
         }
+        if (timing) {
+            long long* st = p.stats + 16 * ((long)blockIdx.y * gridDim.x + blockIdx.x);
+            c_epi = clock64() - te0;
+            st[4] = clock64() - tc0; st[5] = c_p1; st[6] = c_a; st[7] = c_b1; st[8] = c_b2; st[9] = c_sync; st[10] = c_epi;
+        }
     }
     if (TC) {
         tcgen05_fence_before();
@@ -646,6 +675,7 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
 }
 
 SmemCfg g_fused_cfg[2];
+long long* g_ipa_stats = nullptr;      // set by dfold_debug_ipa_stats
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -713,6 +743,14 @@ int fused_make_key_map(CUtensorMap* m, const void* base, long rows) {
 
 using namespace dfold;
 
+// Development aid: when `buf` (device, 16 x int64 per CTA of the next fused-IPA launches) is non-null the kernel records, per
+// CTA, cycle counters of its control thread ({total, wait full, wait P ready, wait empty}) and of compute thread 0
+// ({total, pass 1, phase A, B1, B2, barriers, epilogue}) at slots 0-3 and 4-10.
+extern "C" int dfold_debug_ipa_stats(long long* buf) {
+    g_ipa_stats = buf;
+    return 0;
+}
+
 // Fused forward core.  Writes the point and pair columns of the concat buffer and (when p_hi / p_lo are non-null) the
 // bf16 hi/lo probability planes.  With kv_hi / kv_lo (bf16 hi/lo planes of kv [N, H*2C], row stride ldkv, C = 256) the
 // scalar-value columns [0, H*C) are produced in the same kernel on tcgen05 (P stays on the SM); without them they are
@@ -736,6 +774,7 @@ extern "C" int dfold_ipa_fused_fwd(const float* logit0, const float* q_pts, cons
     p.gamma = gamma; p.p_hi = p_hi; p.p_lo = p_lo; p.ldp = ldp; p.cat = out_cat; p.F = F; p.N = N; p.C = C; p.dfold = dfold;
     p.inf = inf; p.eps = eps;
     { const char* e = getenv("DFOLD_IPA_DEBUG_SKIP"); p.skip = e ? atoi(e) : 0; }
+    p.stats = g_ipa_stats;
     dim3 grid((unsigned)cdiv(N, FTI), (unsigned)F);
     CUtensorMap maps[4];
     memset(maps, 0, sizeof(maps));

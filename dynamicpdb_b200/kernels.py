@@ -26,6 +26,7 @@ _SIGS = {
     "dfold_abi_version": "",
     "dfold_capture_id": "pp",
     "dfold_debug_gemm_stats": "p",
+    "dfold_debug_ipa_stats": "p",
     "dfold_split2d": "plllipl" + "ppll" + "ppll" + "pp",
     "dfold_conv_weight_prep": "piii" + "ppl" + "ppl" + "p",
     "dfold_taps_to_param": "piiipp",
@@ -55,6 +56,7 @@ _SIGS = {
     "dfold_score_bwd": "ppppp" + "pidddd" + "ffpil" + "ppi" + "pp" + "p",
     "dfold_frames_to_atoms_fwd": "pippp" + "pppppp" + "ppp" + "lp",
     "dfold_reverse_step": "ppppi" + "ppp" + "dddddd" + "iii" + "pp" + "llp",
+    "dfold_loss_fwd": "pppppppppppp" + "ii" + "dddd" + "ii" + "pppp" + "p",
     "dfold_quat_mul_fwd": "ppplip",
     "dfold_quat_mul_bwd": "ppppplip",
     "dfold_rot_compose_fwd": "pppp" + "pp" + "liip",

@@ -131,3 +131,51 @@ def surrogate_loss(out: Dict[str, torch.Tensor]) -> torch.Tensor:
     gradient comparison."""
     return ((out["rigids"] ** 2).mean() + (out["unorm_angles"] ** 2).mean()
             + (out["rot_score"].float() ** 2).mean() + (out["trans_score"].float() ** 2).mean())
+
+
+def add_loss_targets(feats: Dict[str, torch.Tensor], *, seed: int = 0, loader_dtypes: bool = True) -> Dict[str, torch.Tensor]:
+    """The extra batch fields ``Experiment.loss_fn`` reads: alternative torsion targets, the
+    ground-truth scores and their scalings (float64 from the numpy diffuser in the reference's loader)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    nf, n_res = feats["res_mask"].shape
+    f64 = torch.float64 if loader_dtypes else torch.float32
+    out = dict(feats)
+    sc = feats["torsion_angles_sin_cos"].cpu()
+    flip = (torch.rand(nf, n_res, 7, generator=g) > 0.5).to(sc.dtype)[..., None]
+    dev = feats["res_mask"].device
+    out["alt_torsion_angles_sin_cos"] = (sc * (1 - 2 * flip)).to(dev)          # pi-periodic alternative (openfold convention)
+    out["rot_score"] = (torch.randn(nf, n_res, 3, generator=g) * 0.7).to(f64).to(dev)
+    out["trans_score"] = torch.randn(nf, n_res, 3, generator=g).to(f64).to(dev)
+    out["rot_score_scaling"] = torch.tensor([0.8], dtype=f64, device=dev)
+    out["trans_score_scaling"] = torch.tensor([1.3], dtype=f64, device=dev)
+    return out
+
+
+def loss_case(seed: int = 11, nf: int = 3, N: int = 14):
+    """Seeded (batch, model_out) pair for the loss fixtures tests/golden/loss.pt (oracle/make_golden.py run_loss): a fixed
+    residue, masked residues, masked torsions and one zero-length predicted torsion vector."""
+    g = torch.Generator().manual_seed(seed)
+    feats = add_loss_targets(make_feats(nf, N, seed=seed, loader_dtypes=True), seed=seed)
+    feats["fixed_mask"][:, 1] = 1
+    feats["res_mask"][:, -2:] = 0
+    feats["torsion_angles_mask"][:, :, 5:] = 0
+    out = {"angles": torch.randn(nf, N, 7, 2, generator=g) * 0.8, "rot_score": torch.randn(nf, N, 3, generator=g, dtype=torch.float64),
+           "rigids": torch.cat([torch.randn(nf, N, 4, generator=g), feats["rigids_0"][..., 4:] + torch.randn(nf, N, 3, generator=g)], dim=-1),
+           "trans_score": torch.randn(nf, N, 3, generator=g), "atom37": torch.randn(nf, N, 37, 3, generator=g)}
+    out["angles"][-1, 0, 0] = 0.0                                     # |u| = 0: the reference's eps-guarded normalisation
+    return feats, out
+
+
+# variants of the loss case: separate axis / angle rotation loss, t below rot_loss_t_threshold, translation loss above the 100 gate
+LOSS_VARIANTS = {"plain": dict(), "separate": dict(separate_rot_loss=True), "t_low": dict(t=0.1), "far": dict(shift=30.0)}
+
+
+def loss_variant(name: str):
+    """(batch, model_out, separate_rot_loss) of one variant."""
+    v = LOSS_VARIANTS[name]
+    feats, out = loss_case()
+    if "t" in v:
+        feats["t"] = torch.tensor([v["t"]], dtype=torch.float64)
+    if "shift" in v:
+        out["rigids"][..., 4:] += v["shift"]
+    return feats, out, v.get("separate_rot_loss", False)

@@ -195,6 +195,8 @@ int dfold_ipa_fused_fwd(const float* logit0, const float* q_pts, const float* kv
                         const float* trans, const float* mask, const float* gamma, uint16_t* p_hi, uint16_t* p_lo, long ldp,
                         const uint16_t* kv_hi, const uint16_t* kv_lo, long ldkv, int F, int N, int H, int C, int Pq, int Pv,
                         int Cp, int dfold, float inf, float eps, float* out_cat, void* stream);
+/* Development aid: per-CTA cycle counters of the next dfold_ipa_fused_fwd launches (16 x int64 per CTA; null = off). */
+int dfold_debug_ipa_stats(long long* buf);
 /* Epilogue backward: d_og [F,N,H,Pv,3], delta [F,H,N], dquat [F,N,4], dtrans [F,N,3]. */
 int dfold_ipa_pre_bwd(const float* quat, const float* trans, int F, int N, int H, int C, int Pv, int Cp, int dfold,
                       const float* out_cat, const float* dcat, float* d_og, float* delta, float* dquat, float* dtrans,
@@ -263,6 +265,18 @@ int dfold_reverse_step(const float* q_t, const float* x_t, const double* rot_sco
                        const float* z_rot, const float* z_trans, const float* mask, double g_rot, double g_trans, double b_t,
                        double dt, double noise_scale, double r3_scale, int center, int diffuse_rot, int diffuse_trans,
                        float* q_out, float* x_out, long F, long N, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training loss (csrc/loss.cu), SURVEY.md 8 f3: value and gradients of Experiment.loss_fn after the model call
+ * (train_DFOLD_dynamics.py:1206-1400; torsion term openfold/utils/loss.py:52-76) in one kernel.  All tensors fp64;
+ * per-residue inputs are those of the LAST frame ([N,...]), the masks cover all nf frames, t / rot_scaling are device
+ * scalars.  out[8] = {loss, rot, trans, torsion (normalised), rot, trans, torsion, final (per-frame)};
+ * d_ang [N,7,2], d_rs [N,3], d_x [N,3] = d out[0] / d (angles, rot_score, translation).
+ * ---------------------------------------------------------------------------------------------------------- */
+int dfold_loss_fwd(const double* ang, const double* a_gt, const double* a_alt, const double* a_mask, const double* rs,
+                   const double* gt_rot, const double* x, const double* x0, const double* res_mask, const double* fixed_mask,
+                   const double* t, const double* rot_scaling, int nf, int N, double w_tor, double w_rot, double w_trans,
+                   double t_thr, int rot_on, int separate, double* out, double* d_ang, double* d_rs, double* d_x, void* stream);
 
 #ifdef __cplusplus
 }

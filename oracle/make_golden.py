@@ -198,7 +198,34 @@ def run_transitions():
     print("transitions ok")
 
 
+def run_loss():
+    """tests/golden/loss.pt: value, aux_data and gradients of the UNMODIFIED Experiment.loss_fn (train_DFOLD_dynamics.py:
+    1181-1400) on seeded model outputs, for the plain / separate-rotation / t-below-threshold / gated (>100) variants."""
+    from types import SimpleNamespace
+    from oracle import dfold_oracle as O
+    res = {}
+    for name in syn.LOSS_VARIANTS:
+        feats, out, separate = syn.loss_variant(name)
+        leaves = {k: out[k].clone().requires_grad_(True) for k in ("angles", "rot_score", "rigids")}
+        model_out = dict(out, **leaves)
+        exp_conf = O.default_exp_conf(separate_rot_loss=separate, bb_atom_loss_weight=1.0,
+                                      bb_atom_loss_t_filter=0.25, dist_mat_loss_weight=1.0, dist_mat_loss_t_filter=0.25,
+                                      aux_loss_weight=0.25)
+        model_conf = SimpleNamespace(cfg_drop_in_train=True, cfg_drop_rate=0.0, embed=SimpleNamespace(embed_self_conditioning=False))
+        exp = ref_shims.reference_experiment(lambda batch, drop_ref=False: model_out, None, model_conf, exp_conf,
+                                             SimpleNamespace(diffuse_rot=True))
+        loss, aux = exp.loss_fn(dict(feats))
+        grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+        res[name] = {"loss": loss.detach(), "aux": {k: a.detach() for k, a in aux.items()},
+                     "grads": {k: (g_.detach() if g_ is not None else None) for k, g_ in zip(leaves, grads)}}
+        print(f"[golden] loss/{name}: {float(loss):.6f}")
+    torch.save(res, os.path.join(OUT, "loss.pt"))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "loss":
+        run_loss()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         run_net_big()
         sys.exit(0)
@@ -206,6 +233,7 @@ if __name__ == "__main__":
         run_reverse()
         sys.exit(0)
     run_reverse()
+    run_loss()
     run_transitions()
     for n, c in NET_CASES.items():
         run_net(n, c)

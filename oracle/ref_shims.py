@@ -98,6 +98,49 @@ def install():
         sys.path.append(REFERENCE_ROOT)
 
 
+_TRAINER_STUBS = [
+    "GPUtil", "hydra", "hydra.core", "hydra.core.hydra_config", "matplotlib", "matplotlib.pyplot", "matplotlib.ticker",
+    "MDAnalysis", "MDAnalysis.analysis", "MDAnalysis.analysis.rms", "MDAnalysis.analysis.align", "MDAnalysis.analysis.rdf",
+    "MDAnalysis.analysis.contacts", "mdtraj", "tmtools", "pdbfixer", "simtk", "simtk.openmm", "simtk.openmm.app",
+    "simtk.openmm.app.internal", "simtk.openmm.app.internal.pdbstructure", "simtk.unit", "openmm", "openmm.app", "openmm.unit",
+    "openmm.app.internal", "openmm.app.internal.pdbstructure",
+]
+
+
+def install_trainer_stubs():
+    """Inert stubs for what the reference's SCRIPTS import on top of the model (train_DFOLD_dynamics.py:17-66: GPUtil,
+    hydra, matplotlib, MDAnalysis, mdtraj, the relax / openmm chain) so that `import train_DFOLD_dynamics` works here and
+    the unmodified Experiment.loss_fn / inference_fn can be called on synthetic batches.  hydra.main becomes the
+    identity decorator (the script decorates its `run(conf)` with it at import time, :1572)."""
+    install()
+    for name in _TRAINER_STUBS:
+        try:
+            __import__(name)
+            continue
+        except Exception:
+            pass
+        parts = name.split(".")
+        for i in range(1, len(parts) + 1):
+            n = ".".join(parts[:i])
+            if n not in sys.modules:
+                m = _stub(n)
+                m.__getattr__ = _lenient_getattr  # type: ignore[attr-defined]
+    import hydra
+    if not callable(getattr(hydra, "main", None)) or isinstance(hydra.main, _Anything):
+        hydra.main = lambda *a, **k: (lambda f: f)
+
+
+def reference_experiment(model, diffuser, model_conf, exp_conf, diff_conf):
+    """An `Experiment` instance of the UNMODIFIED reference trainer with just the attributes loss_fn / inference_fn read,
+    built without running its constructor (which needs hydra configs, data loaders and a GPU census)."""
+    install_trainer_stubs()
+    import train_DFOLD_dynamics as T
+    exp = object.__new__(T.Experiment)
+    exp._model, exp._diffuser = model, diffuser
+    exp._model_conf, exp._exp_conf, exp._diff_conf = model_conf, exp_conf, diff_conf
+    return exp
+
+
 def purge_reference_modules():
     """Drop cached `src.*` / `openfold.*` modules so a different overlay order can be imported."""
     for k in list(sys.modules):

@@ -29,3 +29,14 @@ for train in (True, False):
         for _ in range(10): run(train)
         e1.record(); torch.cuda.synchronize()
         print(f"train={train} skip={skip:2d}: {e0.elapsed_time(e1) / 10:.3f} ms")
+
+# per-CTA cycle counters (dfold_debug_ipa_stats)
+os.environ["DFOLD_IPA_DEBUG_SKIP"] = "0"
+ncta = (N // 32) * F
+buf = torch.zeros(ncta, 16, dtype=torch.int64, device=dev)
+K.lib().dfold_debug_ipa_stats(K._ptr(buf))
+run(True); torch.cuda.synchronize()
+K.lib().dfold_debug_ipa_stats(None)
+m = buf.double().mean(0).tolist()
+names = ["ctl total", "ctl wait full", "ctl wait P ready", "ctl wait empty(+issue)", "cmp total", "pass 1", "phase A", "B1", "B2", "barriers", "epilogue"]
+for n_, v in zip(names, m): print(f"{n_:24s} {v:12.0f} cycles  ({v / 1.9e3:8.1f} us @1.9 GHz)")

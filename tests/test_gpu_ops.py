@@ -63,7 +63,7 @@ def _safe_gate(pre, tau=1e-3):
     return (pre.abs() > tau * pre.abs().max()).to(torch.float64)
 
 
-def check(name, inputs, tol, post=None, wmask=None, **kwargs):
+def check(name, inputs, tol, post=None, wmask=None, grad_tol=None, **kwargs):
     fo = getattr(O, name) if post is None else (lambda *a, **k: post(getattr(O, name)(*a, **k), *a))
     fk = getattr(K, name) if post is None else (lambda *a, **k: post(getattr(K, name)(*a, **k), *a))
     ro, rg = _run(fo, inputs, kwargs, torch.float64, "cpu", wmask)
@@ -79,7 +79,8 @@ def check(name, inputs, tol, post=None, wmask=None, **kwargs):
             continue
         assert a.shape == b.shape, f"{name} grad{i} shape {a.shape} vs {b.shape}"
         err = _rel_err(a, b)
-        assert err < tol, f"{name} grad{i}: rel err {err:.3e} >= {tol}"
+        gt = (grad_tol or {}).get(i, tol)
+        assert err < gt, f"{name} grad{i}: rel err {err:.3e} >= {gt}"
 
 
 def R(*s, grad=True, scale=1.0, seed=None):
@@ -191,7 +192,10 @@ def test_ipa_attention(F, N, H, C, Pq, Pv, Cp, Fs, Fz, dfold, masked):
     # rows of masked QUERY residues see every logit shifted by -1e5: in fp32 (reference and kernel alike) that
     # quantises the logits to 2^-7, so those rows are compared only through the unmasked ones
     post = lambda out, *a: out * a[7][:, :, None]
-    check("ipa_attention", inputs, 2e-4, post=post, Pq=Pq, Pv=Pv, dfold=dfold, inf=1e5, eps=1e-8)
+    # d(gamma) [H] (gradient 7: the mask carries none) is a signed sum over all F*N*N pairs of a head whose terms are orders
+    # of magnitude larger than the sum; the fp32 rounding of the logits alone moves it by ~2e-4 relative, run to run with
+    # the atomic accumulation order
+    check("ipa_attention", inputs, 2e-4, post=post, grad_tol={7: 6e-4}, Pq=Pq, Pv=Pv, dfold=dfold, inf=1e5, eps=1e-8)
 
 
 @pytest.mark.parametrize("F,N,Ci,Co,crop", [(7, 24, 64, 128, 2), (17, 40, 160, 80, 2), (5, 130, 128, 64, 4)])
@@ -243,17 +247,27 @@ def test_score_epilogue(tval, tdtype):
         gq, gx = torch.autograd.grad(loss, [qp, xp])
         return rs.detach().cpu(), ts.detach().cpu(), gq.cpu(), gx.cpu()
 
+    # Where is the reference's own arithmetic (fp32 trigonometry + fp64 series, so3_diffuser.py:71-117) well conditioned?
+    # At small sigma(t) and large relative angle the series cancels catastrophically (at t = 0.03 the fp32 reference is off
+    # the fp64 value by O(1) for omega > 1 rad, where the IGSO(3) density is ~e^-100 and no sample ever lands): residues
+    # whose fp32 reference value deviates from its own fp64 evaluation are not compared (their loss weights are zeroed).
+    with torch.no_grad():
+        r32, _ = O.score_epilogue(q_pred, q_t, None, None, t, _grid(), None, **kw)
+        r64, _ = O.score_epilogue(q_pred.double(), q_t.double(), None, None, t, _grid(), None, **kw)
+    stable = ((r32 - r64).norm(dim=-1) / r64.norm(dim=-1).clamp(min=1.0)) < 1e-5
+    assert stable.float().mean().item() > 0.4, "test data: too few well-conditioned residues"
+    w_r = w_r * stable[..., None]
     ro, to_, gqo, gxo = run(O.score_epilogue, "cpu")
     rk, tk, gqk, gxk = run(K.score_epilogue, DEV)
     assert rk.dtype == torch.float64 and tk.dtype == to_.dtype
-    err = ((ro - rk).norm(dim=-1) / ro.norm(dim=-1).clamp(min=1.0)).max().item()
+    err = (((ro - rk).norm(dim=-1) / ro.norm(dim=-1).clamp(min=1.0)) * stable).max().item()
     assert err < 1e-4, f"rot_score per-residue relative L2 {err:.3e}"
     assert _rel_err(to_.double(), tk.double()) < 2e-6
     assert _rel_err(gxo.double(), gxk.double()) < 2e-6
     assert _rel_err(gqo.double(), gqk.double()) < 2e-4, _rel_err(gqo.double(), gqk.double())
     # rotation score alone (the diffuser API, calc_rot_score)
     r2, none = K.score_epilogue(q_pred.to(DEV), q_t.to(DEV), None, None, t.to(DEV), _grid().to(DEV), None, **kw)
-    assert none is None and (r2.cpu() * mask[..., None] - rk).abs().max().item() < 1e-12 * max(1.0, rk.abs().max().item())
+    assert none is None and ((r2.cpu() * mask[..., None] - rk) * stable[..., None]).abs().max().item() < 1e-12 * max(1.0, rk.abs().max().item())
 
 
 def test_score_epilogue_small_angles():

@@ -22,7 +22,8 @@ def _net(nf, preset):
     return net.cuda()
 
 
-def test_graph_replay_matches_eager_steps():
+def test_graph_replay_matches_eager_steps(monkeypatch):
+    monkeypatch.setenv("DFOLD_GEMM_NO_SPLITK", "1")      # two runs are compared: keep the GEMM accumulation order fixed
     nf, N = 3, 24
     feats = {k: v.cuda() for k, v in syn.make_feats(nf, N, seed=4).items()}
     base = _net(nf, syn.PRESET_TINY)
@@ -41,7 +42,7 @@ def test_graph_replay_matches_eager_steps():
     # gradients of every step agree (parameters themselves are not compared element-wise: Adam turns the noise-level
     # gradients of mathematically gradient-free parameters, e.g. linear_b.bias, into +-lr moves of arbitrary sign)
     for ga, gb in zip(runs[True][2], runs[False][2]):
-        assert ((ga - gb).norm() / gb.norm()).item() < 2e-3
+        assert ((ga - gb).norm() / gb.norm()).item() < 5e-3      # the IPA backward still accumulates dV / d(gamma) atomically
     # parameters that receive no gradient (dead-output embedder, linear_rbf) are not moved by Adam
     for k, v in base.state_dict().items():
         if k.startswith("embedding_layer.") or "linear_rbf" in k:
