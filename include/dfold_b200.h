@@ -278,6 +278,18 @@ int dfold_loss_fwd(const double* ang, const double* a_gt, const double* a_alt, c
                    const double* t, const double* rot_scaling, int nf, int N, double w_tor, double w_rot, double w_trans,
                    double t_thr, int rot_on, int separate, double* out, double* d_ang, double* d_rs, double* d_x, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Input featurisation of a trajectory window (csrc/featurize.cu), SURVEY.md 8 f4: atom37 coordinates [nf,N,37,3] ->
+ * rigids_0 [nf,N,7] (backbone frame as quaternion wxyz + CA; replaces atom37_to_frames group 0 + rot_to_quat's CPU
+ * eigh, openfold/data/data_transforms.py:755-842, openfold/utils/rigid_utils.py:208-227), torsion sin/cos, the
+ * pi-periodic alternative and the mask [nf,N,7,(2)] in fp64 (data_transforms.py:923-1088), as the reference loader
+ * computes them per sample on the host (src/data/Dfold_data_loader_dynamic.py:192-259, :323-330).
+ * Tables: chi_idx [21,4,4] int64, chi_mask / chi_pi [21,4] fp32 (dynamicpdb_b200/data/residue_tables.npz).
+ * ---------------------------------------------------------------------------------------------------------- */
+int dfold_featurize_window(const float* pos, const float* atom_mask, const long* aatype, const long* chi_idx,
+                           const float* chi_mask, const float* chi_pi, int nf, int N, float* rigids, double* tor, double* alt,
+                           double* tmask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

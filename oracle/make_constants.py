@@ -1,4 +1,4 @@
-"""Dump the six numeric residue tables the score-network epilogue reads (SURVEY.md §2 row 17:
+"""Dump the numeric residue tables the score-network epilogue reads (SURVEY.md §2 row 17:
 "constants are *read* by the hot path; import as-is") into dynamicpdb_b200/data/residue_tables.npz,
 so the product and the oracle run on the GPU box where /root/reference does not exist.
 
@@ -20,6 +20,7 @@ from oracle import ref_shims  # noqa: E402
 ref_shims.install()
 from src.data import residue_constants as src_rc  # noqa: E402
 from openfold.np import residue_constants as of_rc  # noqa: E402
+from openfold.data.data_transforms import get_chi_atom_indices  # noqa: E402
 
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                    "dynamicpdb_b200", "data", "residue_tables.npz")
@@ -31,6 +32,10 @@ np.savez_compressed(
     atom14_pos=np.asarray(src_rc.restype_atom14_rigid_group_positions, dtype=np.float32),    # [21,14,3]
     atom37_to_atom14=np.asarray(of_rc.RESTYPE_ATOM37_TO_ATOM14, dtype=np.int64),             # [21,37]
     atom37_mask=np.asarray(of_rc.RESTYPE_ATOM37_MASK, dtype=np.float32),                     # [21,37]
+    # input featurisation (openfold/data/data_transforms.py:895-919, :1001-1003, :1068-1070)
+    chi_atom_indices=np.asarray(get_chi_atom_indices(), dtype=np.int64),                     # [21,4,4]
+    chi_angles_mask=np.asarray(list(of_rc.chi_angles_mask) + [[0.0] * 4], dtype=np.float32), # [21,4]
+    chi_pi_periodic=np.asarray(of_rc.chi_pi_periodic, dtype=np.float32),                     # [21,4]
 )
 # sanity: the two copies of the tables in the reference agree
 assert np.array_equal(src_rc.restype_rigid_group_default_frame, of_rc.restype_rigid_group_default_frame)

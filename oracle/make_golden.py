@@ -222,7 +222,37 @@ def run_loss():
     torch.save(res, os.path.join(OUT, "loss.pt"))
 
 
+def run_loader():
+    """tests/golden/loader.pt: what the UNMODIFIED loader computes for one window of a synthetic trajectory written in the
+    reference's on-disk formats: PdbDataset._process_csv_row (src/data/Dfold_data_loader_dynamic.py:192-259) and the
+    rigids_0 lines of __getitem__ (:323-330), training-mode window selection with numpy seed 5."""
+    import tempfile
+    from types import SimpleNamespace
+    import numpy as np
+    from oracle import synth_traj
+    ref_shims.install_trainer_stubs()
+    from src.data import Dfold_data_loader_dynamic as L
+    traj = synth_traj.make_trajectory()
+    with tempfile.TemporaryDirectory() as d:
+        row = synth_traj.write_files(traj, d)
+        ds = object.__new__(L.PdbDataset)
+        ds._is_training = True
+        ds._data_conf = SimpleNamespace(frame_time=3, keep_first=8, frame_sample_step=2, fix_sample_start=0)
+        np.random.seed(5)
+        feats = ds._process_csv_row(row[0], row[1], row[2], None)
+    rig = RefRU.Rigid.from_tensor_4x4(feats["rigidgroups_0"])[:, :, 0]
+    res = {k: feats[k].clone() for k in ("aatype", "seq_idx", "res_mask", "torsion_angles_sin_cos", "alt_torsion_angles_sin_cos",
+                                         "torsion_angles_mask", "force", "vel")}
+    res["rigids_0"] = rig.to_tensor_7()
+    res["rot_0"] = rig.get_rots().get_rot_mats()
+    torch.save(res, os.path.join(OUT, "loader.pt"))
+    print("[golden] loader:", {k: tuple(v.shape) for k, v in res.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "loader":
+        run_loader()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "loss":
         run_loss()
         sys.exit(0)
@@ -234,6 +264,7 @@ if __name__ == "__main__":
         sys.exit(0)
     run_reverse()
     run_loss()
+    run_loader()
     run_transitions()
     for n, c in NET_CASES.items():
         run_net(n, c)
