@@ -263,21 +263,25 @@ def time_ipa_core(dev, nf, N, iters=20):
     gamma = torch.rand(H, device=dev, generator=g) * 0.2 + 0.05
     alg = 4.0 * (nf * N * (H * (4 * C + 3 * (2 * Pq + Pv) + 8 * Pv + Cp) + 8) + N * N * (H + Cp))
 
-    def run():
-        with torch.no_grad():
-            return K.ipa_attention(logit0, kv, q_pts, kv_pts, pair, quat, trans, mask, gamma, Pq=Pq, Pv=Pv, dfold=True,
-                                   inf=1e5, eps=1e-8)
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    K.LAUNCH_COUNT = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters, alg, K.LAUNCH_COUNT // iters
+    def run(train):
+        q = q_pts.detach().requires_grad_(train)      # training forward: the op also writes the probability planes for backward
+        with torch.set_grad_enabled(train):
+            return K.ipa_attention(logit0, kv, q, kv_pts, pair, quat, trans, mask, gamma, Pq=Pq, Pv=Pv, dfold=True,
+                                   inf=1e5, eps=1e-8).detach()
+    res = {}
+    for train in (True, False):
+        for _ in range(3):
+            run(train)
+        torch.cuda.synchronize()
+        K.LAUNCH_COUNT = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            run(train)
+        e1.record()
+        torch.cuda.synchronize()
+        res[train] = (e0.elapsed_time(e1) / iters, K.LAUNCH_COUNT // iters)
+    return res[True][0], alg, res[True][1], res[False][0]
 
 
 def _fresh_net(nf, dev):
@@ -344,7 +348,7 @@ def extra_configs(dev, graph):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        ipa_ms, alg, _ = time_ipa_core(dev, nf, N, iters=5)
+        ipa_ms, alg, _, _ = time_ipa_core(dev, nf, N, iters=5)
         out["long_chain_1024"] = {
             "workload": "configs[4]: training step fwd+bwd+Adam, N_res=1024, 8 frames, 1 GPU", "ms_per_step": ms,
             "frames_per_s": nf / (ms * 1e-3), "cuda_graph": ts.graph is not None,
@@ -523,7 +527,7 @@ def run_ours(args):
                 "note": "achieved counts fp32-equivalent FLOPs; the split issues 3 bf16 MMAs per product, so frac <= 1/3"}
     roof_ipa = None
     try:
-        ipa_ms, ipa_alg, ipa_launches = time_ipa_core(dev, nf, N)
+        ipa_ms, ipa_alg, ipa_launches, ipa_infer_ms = time_ipa_core(dev, nf, N)
         ach = ipa_alg / ipa_ms / 1e6
         in_step = None
         if "ipa_fwd" in agg:
@@ -533,12 +537,12 @@ def run_ours(args):
         roof_ipa = {"kernel": "ipa_fused_fwd_kernel + tcgen05 P.V (fused IPA forward core, SURVEY.md 8d)", "bound": "hbm",
                     "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "peak_source": hbm_src,
                     "traffic": traffic.get("ipa_fwd_dram_bytes_per_launch"), "algorithmic_bytes": ipa_alg,
-                    "avg_launch_ms": ipa_ms, "kernels_per_call": ipa_launches, "calls_per_step": 4,
+                    "avg_launch_ms": ipa_ms, "inference_ms": ipa_infer_ms, "kernels_per_call": ipa_launches, "calls_per_step": 4,
                     "share_of_step": 4 * ipa_ms / ms, "in_step": in_step,
                     "timed_in": "20 back-to-back calls of the op at the benchmark shape, CUDA events on the launching stream, "
                                 "inputs (659 MB) larger than L2",
-                    "note": "algorithmic bytes per SURVEY.md 8(d) (per-frame q/k/v formulation); the training forward also "
-                            "writes the bf16 probability planes (134 MB) the backward GEMMs read"}
+                    "note": "training forward (also writes the 134 MB of bf16 probability planes the backward GEMMs read); inference_ms = "
+                            "the same kernel without the planes; algorithmic bytes per SURVEY.md 8(d) (per-frame q/k/v formulation)"}
     except Exception as e:      # noqa: BLE001
         roof_ipa = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 

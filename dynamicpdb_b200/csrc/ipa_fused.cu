@@ -185,7 +185,8 @@ constexpr int kSV = FTJ * FH * PV3;            // value points of a tile [j][h][
 constexpr int kSP = FTI * SPS;                 // probabilities         [i][hp][j][2]
 constexpr int kSRow = 2 * FTI;                 // per row {clamped row * N (int), mask_i * inf}
 constexpr int kSStat = 2 * FH * FTI;           // per (h, row) {m, 1 / l}
-constexpr int kStage = FTI * 768;              // epilogue staging of the point features
+constexpr int SST = 772;                       // staging row stride (floats): 16-byte aligned, 4-way instead of 32-way conflicts
+constexpr int kStage = FTI * SST;              // epilogue staging of the point features
 constexpr int kSK = FTJ * FH * PQ3;             // key points of a tile [h][j][24] (8 TMA boxes): pass 1, in the s_v / s_p space
 constexpr int kWork = kSQ + kSV + kSP;
 constexpr int kPB = 65536;                     // tensor-core variant: bf16 P tiles  [h][hi|lo][32 rows][128 B]   (bytes)
@@ -496,35 +497,43 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
             if (TC && tid == 0) mbar_arrive(pready_bar(par));
             // ---- phase B1: pair aggregation, warp = 2 rows, lane = pair channel ----
             if (!(p.skip & 4)) {
+                // eight batches of 8 keys (2 rows x 4 quarters of the tile); the z loads of batch b + 1 are in flight while
+                // batch b is accumulated (L2 latency, not bandwidth, bounds this phase)
                 const bool full = j0 + FTJ <= N;
+                const float* zrow0 = p.pair + ((long)__float_as_int(s_row[4 * warp]) + j0) * FCP + lane;
+                const float* zrow1 = p.pair + ((long)__float_as_int(s_row[4 * warp + 2]) + j0) * FCP + lane;
+                auto load_z = [&](int bt, float (&z)[8]) {
+                    const float* zr = (bt >> 2) ? zrow1 : zrow0;
+                    const int jb = (bt & 3) * 8;
+                    if (full) {
 #pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const int r = warp * 2 + a;
-                    const float* zrow = p.pair + ((long)__float_as_int(s_row[2 * r]) + j0) * FCP + lane;
-                    const float* prow = s_p + r * SPS;
+                        for (int q = 0; q < 8; ++q) z[q] = __ldg(zr + (jb + q) * FCP);
+                    } else {
 #pragma unroll
-                    for (int jb = 0; jb < FTJ; jb += 16) {
-                        float z[16];
-                        if (full) {
+                        for (int q = 0; q < 8; ++q) z[q] = __ldg(zr + (min(j0 + jb + q, N - 1) - j0) * FCP);
+                    }
+                };
+                float zc[8], zn[8];
+                load_z(0, zc);
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) z[q] = __ldg(zrow + (jb + q) * FCP);
-                        } else {
+                for (int bt = 0; bt < 8; ++bt) {
+                    if (bt < 7) load_z(bt + 1, zn);
+                    const int a = bt >> 2, jb = (bt & 3) * 8;
+                    const float* prow = s_p + (warp * 2 + a) * SPS;
 #pragma unroll
-                            for (int q = 0; q < 16; ++q) z[q] = __ldg(zrow + (min(j0 + jb + q, N - 1) - j0) * FCP);
-                        }
+                    for (int q = 0; q < 8; q += 2) {
+                        const u64 zz0 = pack2(zc[q], zc[q]), zz1 = pack2(zc[q + 1], zc[q + 1]);
+                        ulonglong2 pp[4];
 #pragma unroll
-                        for (int q = 0; q < 16; q += 2) {
-                            const u64 zz0 = pack2(z[q], z[q]), zz1 = pack2(z[q + 1], z[q + 1]);
-                            ulonglong2 pp[4];
+                        for (int b = 0; b < 4; ++b) pp[b] = *reinterpret_cast<const ulonglong2*>(prow + b * (2 * FTJ) + (jb + q) * 2);
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) pp[b] = *reinterpret_cast<const ulonglong2*>(prow + b * (2 * FTJ) + (jb + q) * 2);
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                accp[a][b] = fma2(pp[b].x, zz0, accp[a][b]);
-                                accp[a][b] = fma2(pp[b].y, zz1, accp[a][b]);
-                            }
+                        for (int b = 0; b < 4; ++b) {
+                            accp[a][b] = fma2(pp[b].x, zz0, accp[a][b]);
+                            accp[a][b] = fma2(pp[b].y, zz1, accp[a][b]);
                         }
                     }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) zc[q] = zn[q];
                 }
             }
             if (timing) { const long long n = clock64(); c_b1 += n - tt; tt = n; }
@@ -632,7 +641,7 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
 #pragma unroll
                 for (int c = 0; c < PV3 / 4; ++c) unpack2(src[c], g[2 * c], g[2 * c + 1]);
             }
-            float* srow = stage + r * 768;
+            float* srow = stage + r * SST;
 #pragma unroll
             for (int pt = 0; pt < FPV / 2; ++pt) {
                 const float gx = g[3 * pt], gy = g[3 * pt + 1], gz = g[3 * pt + 2];
@@ -654,7 +663,7 @@ ipa_fused_fwd_kernel(const FusedParams p, const __grid_constant__ CUtensorMap ma
                 const int c4 = e % 96, sg = (e / 96) % nseg, r = e / (96 * nseg);
                 const int i = i0 + r;
                 if (i >= N) continue;
-                const float4 v = *reinterpret_cast<const float4*>(stage + r * 768 + sg * 384 + c4 * 4);
+                const float4 v = *reinterpret_cast<const float4*>(stage + r * SST + sg * 384 + c4 * 4);
                 float* dst = p.cat + (fN + i) * D + (sg ? offG : offLoc) + c4 * 4;
                 *reinterpret_cast<float4*>(dst) = v;
             }
