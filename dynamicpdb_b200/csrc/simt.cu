@@ -102,6 +102,30 @@ __global__ void __launch_bounds__(256) conv_weight_prep_kernel(const float* __re
         for (int e = threadIdx.x; e < ni * T; e += blockDim.x) sm[oo * row + e] = split_pack(src[e]);
     }
     __syncthreads();
+    if (no == 32 && ni == 32 && (ldi & 3) == 0 && (d_hi == nullptr || (ldo_ & 3) == 0)) {
+        // full tile: 8-byte stores (4 bf16 of one plane), 8 lanes per 64-byte row
+        for (int e = threadIdx.x; e < T * 32 * 8; e += blockDim.x) {
+            const int q = e & 7, oo = (e >> 3) & 31, t = e >> 8;
+            uint32_t pk[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pk[c] = sm[oo * row + (4 * q + c) * T + t];
+            const long fo = ((long)t * O + o0 + oo) * ldi + i0 + 4 * q;
+            *reinterpret_cast<uint2*>(f_hi + fo) = make_uint2((pk[0] >> 16) | (pk[1] & 0xffff0000u), (pk[2] >> 16) | (pk[3] & 0xffff0000u));
+            *reinterpret_cast<uint2*>(f_lo + fo) = make_uint2((pk[0] & 0xffffu) | (pk[1] << 16), (pk[2] & 0xffffu) | (pk[3] << 16));
+        }
+        if (d_hi) {
+            for (int e = threadIdx.x; e < T * 32 * 8; e += blockDim.x) {
+                const int q = e & 7, ii = (e >> 3) & 31, t = e >> 8;
+                uint32_t pk[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) pk[c] = sm[(4 * q + c) * row + ii * T + t];
+                const long dofs = ((long)(T - 1 - t) * I + i0 + ii) * ldo_ + o0 + 4 * q;
+                *reinterpret_cast<uint2*>(d_hi + dofs) = make_uint2((pk[0] >> 16) | (pk[1] & 0xffff0000u), (pk[2] >> 16) | (pk[3] & 0xffff0000u));
+                *reinterpret_cast<uint2*>(d_lo + dofs) = make_uint2((pk[0] & 0xffffu) | (pk[1] << 16), (pk[2] & 0xffffu) | (pk[3] << 16));
+            }
+        }
+        return;
+    }
     // forward planes: (t, o) rows, i contiguous
     for (int e = threadIdx.x; e < T * 32 * 32; e += blockDim.x) {
         const int ii = e & 31, oo = (e >> 5) & 31, t = e >> 10;
@@ -477,4 +501,53 @@ extern "C" int dfold_row_layernorm_bwd(const float* x, const float* w, const flo
     DFOLD_REQUIRE(rows > 0 && C > 0, "dfold_row_layernorm_bwd: empty input");
     row_ln_bwd_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, as_stream(stream)>>>(x, w, dy, stats, dx, dw, db, rows, C);
     return check_launch("row_ln_bwd_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Adam (amsgrad) over flat fp32 buffers: the optimizer of the reference trainer (torch.optim.Adam(amsgrad=True),
+// train_DFOLD_dynamics.py:412) for the graph-captured step of dynamicpdb_b200/train_step.py.  One pass over
+// {param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq}: 36 bytes per element instead of the ~90 of the multi-tensor kernels.
+// `step` lives on the device (float; incremented by adam_tick_kernel) so the update is CUDA-graph capturable.
+// ---------------------------------------------------------------------------------------------------
+namespace dfold {
+namespace {
+__global__ void adam_tick_kernel(float* step) { *step += 1.f; }
+
+__global__ void __launch_bounds__(256) adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                           float* __restrict__ v, float* __restrict__ vmax, long n4,
+                                                           const float* __restrict__ step, float lr, float b1, float b2, float eps) {
+    const float t = *step;
+    const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
+    const float step_size = lr / bc1, inv_bc2_sqrt = 1.f / sqrtf(bc2);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 P = reinterpret_cast<float4*>(p)[i];
+        const float4 G = reinterpret_cast<const float4*>(g)[i];
+        float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i], X = reinterpret_cast<float4*>(vmax)[i];
+        float* pp = &P.x; const float* gg = &G.x; float* mm = &M.x; float* vv = &V.x; float* xx = &X.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            mm[c] = mm[c] + (gg[c] - mm[c]) * (1.f - b1);                  // exp_avg.lerp_(grad, 1 - beta1)
+            vv[c] = vv[c] * b2 + (1.f - b2) * gg[c] * gg[c];
+            xx[c] = fmaxf(xx[c], vv[c]);
+            pp[c] = pp[c] - step_size * mm[c] / (sqrtf(xx[c]) * inv_bc2_sqrt + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = P;
+        reinterpret_cast<float4*>(m)[i] = M;
+        reinterpret_cast<float4*>(v)[i] = V;
+        reinterpret_cast<float4*>(vmax)[i] = X;
+    }
+}
+}  // namespace
+}  // namespace dfold
+
+// n must be a multiple of 4 and the buffers 16-byte aligned (train_step.py pads its flat buffers).
+extern "C" int dfold_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
+                                  float* step, float lr, float beta1, float beta2, float eps, void* stream) {
+    DFOLD_REQUIRE(n > 0 && n % 4 == 0, "dfold_adam_amsgrad: n must be a positive multiple of 4");
+    cudaStream_t st = dfold::as_stream(stream);
+    dfold::adam_tick_kernel<<<1, 1, 0, st>>>(step);
+    const long n4 = n / 4;
+    const int blocks = (int)(dfold::cdiv(n4, 256) < 148 * 16 ? dfold::cdiv(n4, 256) : 148 * 16);
+    dfold::adam_amsgrad_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n4, step, lr, beta1, beta2, eps);
+    return dfold::check_launch("adam_amsgrad_kernel");
 }

@@ -34,13 +34,33 @@ class TrainStep:
         self.params = [p for p in net.parameters() if p.requires_grad]
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        padded = (total + 3) // 4 * 4                      # the fused optimizer runs float4-wide over the flat buffers
+        self.flat_grad = torch.zeros(padded, dtype=torch.float32, device=dev)
+        # Adam(amsgrad) as the reference trainer (train_DFOLD_dynamics.py:412).  Default: ONE fused kernel over flat
+        # parameter / gradient / moment buffers (csrc/simt.cu adam_amsgrad_kernel, step counter on the device); with
+        # DFOLD_TORCH_ADAM=1: torch.optim.Adam(capturable, foreach) on the same gradient views.
+        self.fused_adam = os.environ.get("DFOLD_TORCH_ADAM", "0") != "1"
+        self.lr = lr
+        if self.fused_adam:
+            self.flat_param = torch.zeros(padded, dtype=torch.float32, device=dev)
         off = 0
-        for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        # Adam(amsgrad) as the reference trainer (train_DFOLD_dynamics.py:412); capturable keeps the step count on device
-        self.opt = torch.optim.Adam(self.params, lr=lr, amsgrad=True, capturable=True, foreach=True)
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                if self.fused_adam:
+                    self.flat_param[off:off + n].copy_(p.reshape(-1))
+                    p.data = self.flat_param[off:off + n].view_as(p)       # the module's parameters become views of the flat buffer
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+                off += n
+        if self.fused_adam:
+            self.exp_avg = torch.zeros_like(self.flat_param)
+            self.exp_avg_sq = torch.zeros_like(self.flat_param)
+            self.max_exp_avg_sq = torch.zeros_like(self.flat_param)
+            self.step_count = torch.zeros((), dtype=torch.float32, device=dev)
+            self.opt = None
+            _kernels.invalidate_weight_cache()
+        else:
+            self.opt = torch.optim.Adam(self.params, lr=lr, amsgrad=True, capturable=True, foreach=True)
         self.static = {k: v.clone() for k, v in example_feats.items()}
         self.loss = torch.zeros((), dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
@@ -51,7 +71,7 @@ class TrainStep:
         # the caller handed in, so both are snapshotted here and restored after capture.
         with torch.no_grad():
             saved_params = [p.detach().clone() for p in self.params]
-        saved_opt = copy.deepcopy(self.opt.state_dict())
+        saved_opt = copy.deepcopy(self.opt.state_dict()) if self.opt is not None else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -81,18 +101,22 @@ class TrainStep:
         with torch.no_grad():
             for p, v in zip(self.params, saved_params):
                 p.copy_(v)
-            fresh = not saved_opt["state"]
-            for i, p in enumerate(self.params):
-                st = self.opt.state.get(p)
-                if not st:
-                    continue
-                old = None if fresh else saved_opt["state"].get(i)
-                for k, v in st.items():
-                    if torch.is_tensor(v):
-                        if old is not None and k in old:
-                            v.copy_(old[k].to(v.device))
-                        else:
-                            v.zero_()
+            if self.opt is None:
+                for t in (self.exp_avg, self.exp_avg_sq, self.max_exp_avg_sq, self.step_count):
+                    t.zero_()
+            else:
+                fresh = not saved_opt["state"]
+                for i, p in enumerate(self.params):
+                    st = self.opt.state.get(p)
+                    if not st:
+                        continue
+                    old = None if fresh else saved_opt["state"].get(i)
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            if old is not None and k in old:
+                                v.copy_(old[k].to(v.device))
+                            else:
+                                v.zero_()
             self.flat_grad.zero_()
         _kernels.invalidate_weight_cache()
         torch.cuda.synchronize()
@@ -105,8 +129,18 @@ class TrainStep:
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
             self.flat_grad.mul_(1.0 / self.world)
-        self.opt.step()
+        self.optimizer_step()
         self.loss.copy_(loss.detach().float())
+
+    def optimizer_step(self):
+        if self.opt is not None:
+            self.opt.step()
+            return
+        K = _kernels
+        K._check(K.lib().dfold_adam_amsgrad(K._ptr(self.flat_param), K._ptr(self.flat_grad), K._ptr(self.exp_avg),
+                                            K._ptr(self.exp_avg_sq), K._ptr(self.max_exp_avg_sq), self.flat_param.numel(),
+                                            K._ptr(self.step_count), self.lr, 0.9, 0.999, 1e-8, K._stream()), "dfold_adam_amsgrad")
+        K.invalidate_weight_cache()                    # the weights moved without touching their version counters
 
     def load(self, feats: Dict[str, torch.Tensor]):
         """Copy a new window into the static input buffers (H2D when `feats` is pinned host memory)."""

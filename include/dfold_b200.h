@@ -290,6 +290,11 @@ int dfold_featurize_window(const float* pos, const float* atom_mask, const long*
                            const float* chi_mask, const float* chi_pi, int nf, int N, float* rigids, double* tor, double* alt,
                            double* tmask, void* stream);
 
+/* Adam (amsgrad) of the reference trainer (torch.optim.Adam(amsgrad=True), train_DFOLD_dynamics.py:412) in one pass over
+ * flat fp32 buffers of n elements (n % 4 == 0); `step` is a device float incremented by the call (graph capturable). */
+int dfold_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
+                       float* step, float lr, float beta1, float beta2, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,3 +63,26 @@ def test_long_chain_1024_residues_forward_backward():
     assert out["rigids"].shape == (nf, N, 7) and out["atom37"].shape == (nf, N, 37, 3)
     g = net.score_model.trunk["ipa_0"].linear_q.weight.grad
     assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0
+
+
+def test_fused_adam_matches_torch_adam_amsgrad():
+    """csrc/simt.cu adam_amsgrad_kernel == torch.optim.Adam(amsgrad=True) (the reference trainer's optimizer,
+    train_DFOLD_dynamics.py:412) over several steps, including zero gradients (parameters stay put)."""
+    from dynamicpdb_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 4096 + 8
+    p0 = torch.randn(n, device="cuda", generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, amsgrad=True)
+    p = p0.clone()
+    m, v, vm = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros((), device="cuda")
+    for it in range(6):
+        grad = torch.randn(n, device="cuda", generator=g) * (10.0 ** (it - 3))
+        grad[:100] = 0
+        ref.grad = grad.clone()
+        opt.step()
+        K._check(K.lib().dfold_adam_amsgrad(K._ptr(p), K._ptr(grad), K._ptr(m), K._ptr(v), K._ptr(vm), n, K._ptr(step),
+                                            1e-3, 0.9, 0.999, 1e-8, K._stream()), "dfold_adam_amsgrad")
+        assert (p - ref.detach()).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item()), it
+    assert torch.equal(p[:100], p0[:100]) and float(step) == 6.0
