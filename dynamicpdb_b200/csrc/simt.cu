@@ -85,6 +85,41 @@ __global__ void split2d_kernel(const float* __restrict__ x, long R, long C, long
     }
 }
 
+// Row-major fast path of split2d (no transposed planes, no column sums, 16-byte aligned rows): one thread = four consecutive
+// columns, float4 in, 8 bytes of each plane out.
+__global__ void __launch_bounds__(256) split2d_vec_kernel(const float* __restrict__ x, long R, long C, long ld, int pre_relu,
+                                                          const float* __restrict__ gate, long ldg, uint16_t* __restrict__ hi,
+                                                          uint16_t* __restrict__ lo, long ldo, long c4n) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * c4n) return;
+    const long r = idx / c4n, c = (idx % c4n) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c + 4 <= C) {
+        const float4 t = *reinterpret_cast<const float4*>(x + r * ld + c);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        if (gate) {
+            const float4 g = *reinterpret_cast<const float4*>(gate + r * ldg + c);
+            v[0] = g.x > 0.f ? v[0] : 0.f; v[1] = g.y > 0.f ? v[1] : 0.f; v[2] = g.z > 0.f ? v[2] : 0.f; v[3] = g.w > 0.f ? v[3] : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c + k < C) {
+                v[k] = x[r * ld + c + k];
+                if (gate) v[k] = (gate[r * ldg + c + k] > 0.f) ? v[k] : 0.f;
+            }
+    }
+    if (pre_relu) {                     // relu and the gate commute: relu(gate ? v : 0) == gate ? relu(v) : 0
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pk[k] = split_pack(v[k]);
+    *reinterpret_cast<uint2*>(hi + r * ldo + c) = make_uint2((pk[0] >> 16) | (pk[1] & 0xffff0000u), (pk[2] >> 16) | (pk[3] & 0xffff0000u));
+    *reinterpret_cast<uint2*>(lo + r * ldo + c) = make_uint2((pk[0] & 0xffffu) | (pk[1] << 16), (pk[2] & 0xffffu) | (pk[3] << 16));
+}
+
 // conv weight w[O][I][T] (T = taps, contiguous) ->
 //   fwd planes   [T][O][ldi]   (K = I contiguous)
 //   dgrad planes [T][I][ldo_]  (K = O contiguous), tap index flipped (T-1-t)
@@ -426,6 +461,13 @@ extern "C" int dfold_split2d(const float* x, long R, long C, long ld, int pre_re
     // the grid covers the padded extents so the padding columns/rows are written as zeros
     const long cols = (hi && cpad > C) ? cpad : C;
     const long rows = (hi_t && rpad > R) ? rpad : R;
+    if (hi && !hi_t && !colsum && (ld & 3) == 0 && (ldo & 3) == 0 && (cpad & 3) == 0 && (!gate || (ldg & 3) == 0) &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gate)) & 15) == 0 &&
+        ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0) {
+        const long c4n = cpad / 4, n = R * c4n;
+        split2d_vec_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(x, R, C, ld, pre_relu, gate, ldg, hi, lo, ldo, c4n);
+        return check_launch("split2d_vec_kernel");
+    }
     dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32));
     split2d_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, R, C, ld, pre_relu, gate, ldg, hi, lo, ldo, cpad, hi_t, lo_t, ldt, rpad, colsum);
     return check_launch("split2d_kernel");
