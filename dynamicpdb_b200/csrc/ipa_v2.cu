@@ -465,6 +465,7 @@ extern "C" int dfold_ipa_ds_bwd(V2_ARGS, const float* dcat, const float* d_og, c
     dim3 grid((unsigned)cdiv(N, TI), (unsigned)H, (unsigned)F);
     ipa_ds_kernel<<<grid, 256, smem, st>>>(p, dcat, d_og, delta, dP, Tz, dS, dgamma);
     if (check_launch("ipa_ds_kernel")) return 1;
+    if (dq_pts == nullptr) return 0;       // the caller computes the point gradients as tensor-core contractions over dS
     const size_t smem2 = sizeof(float) * (size_t)(32 * PQ3 + 32 * (PQ3 + 1));
     ipa_pts_grad_kernel<<<grid, 256, smem2, st>>>(p, dS, dq_pts, dkv_pts, 0);
     ipa_pts_grad_kernel<<<grid, 256, smem2, st>>>(p, dS, dq_pts, dkv_pts, 1);

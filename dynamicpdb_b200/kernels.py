@@ -927,10 +927,43 @@ class _IpaAttnTCFn(Function):
         dgamma = torch.zeros(H_, dtype=torch.float32, device=dev)
         dq_pts, dkv_pts = new(*q_pts.shape), new(*kv_pts.shape)
         args = _IpaAttnTCFn._v2args(logit0, q_pts, kv_pts, pair, quat, trans, mask, gamma, p_hi, p_lo, n8, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
+        pts_gemm = PQ3 <= 31 and os.environ.get("DFOLD_IPA_PTS_GEMM", "1") != "0"
         _check(lib().dfold_ipa_ds_bwd(*args, _ptr(dcat), _ptr(d_og), _ptr(delta), _ptr(dP), _ptr(Tz), _ptr(dS), _ptr(dgamma),
-                                      _ptr(dq_pts), _ptr(dkv_pts), _stream()), "dfold_ipa_ds_bwd")
+                                      None if pts_gemm else _ptr(dq_pts), _ptr(dkv_pts), _stream()), "dfold_ipa_ds_bwd")
         del Tz
         del dP
+        if pts_gemm:
+            # Point gradients as two small tensor-core contractions over dS instead of the CUDA-core / LDS-bound pass:
+            #   dq_pts[i] = -gamma (q_i rowsum_i - sum_j dS_ij k_j),   dk_pts[j] = gamma (sum_i dS_ij q_i - colsum_j k_j)
+            # with a ones column appended to the point operands so the row / column sums fall out of the same products.
+            ds_hi, ds_lo = _planes_rows(dS.reshape(F_ * H_ * N_, N_))                                   # [F*H*N, n8]
+            kq = kv_pts.reshape(F_, N_, H_, W)[..., :PQ3]
+            kt = torch.zeros((F_, H_, 32, N_), dtype=torch.float32, device=dev)
+            kt[:, :, :PQ3] = kq.permute(0, 2, 3, 1)
+            kt[:, :, PQ3] = 1.0
+            kt_hi, kt_lo = _planes_rows(kt.reshape(F_ * H_ * 32, N_))                                   # [F*H*32, n8]
+            g1 = new(F_ * H_ * N_, 32)
+            _check(lib().dfold_gemm_bf16x3_batched(
+                _ptr(ds_hi), _ptr(ds_lo), F_ * H_, N_, N_, ds_hi.shape[1], F_ * H_, F_ * H_, 1, 0, N_,
+                _ptr(kt_hi), _ptr(kt_lo), F_ * H_, 32, N_, kt_hi.shape[1], 0, 0, 1, 32,
+                _ptr(g1), 32, F_ * H_ * N_, 1, 0, 1.0, _stream()), "dfold_gemm_bf16x3_batched")
+            qn = torch.zeros((F_, H_, N_, 32), dtype=torch.float32, device=dev)
+            qh = q_pts.reshape(F_, N_, H_, PQ3).permute(0, 2, 1, 3)                                     # [F,H,N,24]
+            qn[..., :PQ3] = qh
+            qn[..., PQ3] = 1.0
+            qn_hi, qn_lo = _planes_rows(qn.reshape(F_ * H_ * N_, 32))
+            g2 = new(F_ * H_, N_, 32)
+            _check(lib().dfold_gemm_wgrad_bf16x3_batched(
+                _ptr(ds_hi), _ptr(ds_lo), N_, N_, F_ * H_, ds_hi.shape[1], N_ * ds_hi.shape[1],
+                _ptr(qn_hi), _ptr(qn_lo), 32, N_, F_ * H_, qn_hi.shape[1], N_ * qn_hi.shape[1],
+                32, 1, N_, F_ * H_, 1, 0, 1, 0, 1, 0,
+                _ptr(g2), 32, N_ * 32, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3_batched")
+            g1 = g1.reshape(F_, H_, N_, 32)
+            gam = gamma.reshape(1, H_, 1, 1)
+            dq = -gam * (qh * g1[..., PQ3:PQ3 + 1] - g1[..., :PQ3])
+            dq_pts.copy_(dq.permute(0, 2, 1, 3).reshape(q_pts.shape))
+            dk = gam * (g2[..., :PQ3].reshape(F_, H_, N_, PQ3) - g2[..., PQ3:PQ3 + 1].reshape(F_, H_, N_, 1) * kq.permute(0, 2, 1, 3))
+            dkv_pts.reshape(F_, N_, H_, W)[..., :PQ3] = dk.permute(0, 2, 1, 3)
         # ---- dV[j,h,c] = sum_{f,i} P[f,h,i,j] dO[f,i,h,c]   (MN-major, split-K over frames, atomic accumulate) ----
         dkv = torch.zeros_like(kv)
         splits = max(1, min(F_, 16))
