@@ -329,6 +329,88 @@ __global__ void __launch_bounds__(256) ipa_ds_kernel(const V2Params p, const flo
     (void)gam;
 }
 
+// Second-generation dS kernel (Pq = 8): the value-point term d_og.v_pts arrives precomputed from the tensor cores (Tog,
+// [F,H,N,N]), each lane keeps its key's 24 coordinates in registers, the query points are broadcast 16 bytes at a time and
+// the squared distance for d(gamma) runs on packed FADD2 / FFMA2 -- 6 shared-memory loads per pair instead of ~120.
+// grid (ceil(N/32), H, F), 256 threads: 4 rows per warp, keys across lanes.
+typedef unsigned long long u64v2;
+__device__ __forceinline__ u64v2 v2_sub2(u64v2 a, u64v2 b) { u64v2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64v2 v2_fma2(u64v2 a, u64v2 b, u64v2 c) { u64v2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__global__ void __launch_bounds__(256) ipa_ds2_kernel(const V2Params p, const float* __restrict__ delta, const float* __restrict__ dPg,
+                                                      const float* __restrict__ Tz, const float* __restrict__ Tog,
+                                                      float* __restrict__ dS, float* __restrict__ dgamma) {
+    __shared__ __align__(16) float s_q[TI * 24];
+    __shared__ __align__(16) float s_k[TJ * 24];
+    __shared__ float s_red[8];
+    const int N = p.N, H = p.H;
+    const int W = 24 + p.Pv * 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.x * TI, h = blockIdx.y, f = blockIdx.z;
+    for (int e = tid; e < TI * 6; e += 256) {
+        const int r = e / 6, c4 = e % 6, i = i0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < N) v = __ldg(reinterpret_cast<const float4*>(p.q_pts + (((long)f * N + i) * H + h) * 24) + c4);
+        reinterpret_cast<float4*>(s_q)[e] = v;
+    }
+    const float* kvp = p.kv_pts + ((long)f * N * H + h) * W;
+    float dl[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+        const int i = i0 + warp * 4 + rr;
+        dl[rr] = (i < N) ? delta[((long)f * H + h) * N + i] : 0.f;
+    }
+    float dgam = 0.f;
+    for (int j0 = 0; j0 < N; j0 += TJ) {
+        __syncthreads();
+        for (int e = tid; e < TJ * 6; e += 256) {
+            const int jj = e / 6, c4 = e % 6, j = j0 + jj;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < N) v = __ldg(reinterpret_cast<const float4*>(kvp + (long)j * H * W) + c4);
+            reinterpret_cast<float4*>(s_k)[e] = v;
+        }
+        __syncthreads();
+        const int j = j0 + lane;
+        if (j >= N) continue;
+        u64v2 k[12];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const ulonglong2 v = reinterpret_cast<const ulonglong2*>(s_k + lane * 24)[c];
+            k[2 * c] = v.x; k[2 * c + 1] = v.y;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = warp * 4 + rr, i = i0 + r;
+            if (i >= N) continue;
+            const long o = (((long)f * H + h) * N + i) * N + j;
+            const long op = (((long)f * H + h) * N + i) * p.ldp + j;
+            const float pv = join_bf16(p.p_hi[op], p.p_lo[op]);
+            const float dp = dPg[o] + Tog[o] + Tz[((long)i * p.F * H + (long)f * H + h) * N + j];
+            const float ds = pv * (dp - dl[rr]);
+            dS[o] = ds;
+            const ulonglong2* q2 = reinterpret_cast<const ulonglong2*>(s_q + r * 24);
+            u64v2 a0 = 0ull;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const ulonglong2 qq = q2[c];
+                const u64v2 d0 = v2_sub2(qq.x, k[2 * c]), d1 = v2_sub2(qq.y, k[2 * c + 1]);
+                a0 = v2_fma2(d0, d0, a0);
+                a0 = v2_fma2(d1, d1, a0);
+            }
+            float x0, x1;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(a0));
+            dgam = fmaf(ds, -0.5f * (x0 + x1), dgam);
+        }
+    }
+    dgam = warp_sum(dgam);
+    if (lane == 0) s_red[warp] = dgam;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        atomicAdd(dgamma + h, t);
+    }
+}
+
 // transpose = 0: dq_pts[f,a=i,h,c] = -gamma * sum_j dS[i][j] (qp_i - kp_j)
 // transpose = 1: dk_pts[f,a=j,h,c] = +gamma * sum_i dS[i][j] (qp_i - kp_j)
 // grid (ceil(N/32), H, F), 256 threads: thread = (self item a = tid/8, component group g = tid%8)
@@ -454,7 +536,7 @@ extern "C" int dfold_ipa_pair_fwd(V2_ARGS, float* out_cat, void* stream) {
 // dS [F,H,N,N] from the GEMM-produced dP [F,H,N,N]; dgamma [H] pre-zeroed.  Then the two point-gradient passes.
 // Tz (nullable): the pair term sum_c dOpair[f,i,h,c] z[i,j,c] precomputed as [N(i)][F*H][N(j)] on the tensor cores.
 extern "C" int dfold_ipa_ds_bwd(V2_ARGS, const float* dcat, const float* d_og, const float* delta, const float* dP,
-                                const float* Tz, float* dS, float* dgamma, float* dq_pts, float* dkv_pts, void* stream) {
+                                const float* Tz, const float* Tog, float* dS, float* dgamma, float* dq_pts, float* dkv_pts, void* stream) {
     V2Params p;
     if (v2_params(p, logit0, logit0_fstride, q_pts, kv_pts, pair, pair_fstride, quat, trans, mask, gamma, p_hi, p_lo, ldp,
                   F, N, H, C, Pq, Pv, Cp, dfold, inf, eps)) return 1;
@@ -463,8 +545,14 @@ extern "C" int dfold_ipa_ds_bwd(V2_ARGS, const float* dcat, const float* d_og, c
     const size_t smem = sizeof(float) * (size_t)(TI * PQ3 + TJ * (W + 1) + TI * PV3 + TI * Cp);
     if (set_smem(ipa_ds_kernel, smem, "ipa_ds")) return 1;
     dim3 grid((unsigned)cdiv(N, TI), (unsigned)H, (unsigned)F);
-    ipa_ds_kernel<<<grid, 256, smem, st>>>(p, dcat, d_og, delta, dP, Tz, dS, dgamma);
-    if (check_launch("ipa_ds_kernel")) return 1;
+    if (Tog != nullptr) {
+        DFOLD_REQUIRE(Pq == 8 && Tz != nullptr, "dfold_ipa_ds_bwd: the precomputed value-point term needs Pq = 8 and Tz");
+        ipa_ds2_kernel<<<grid, 256, 0, st>>>(p, delta, dP, Tz, Tog, dS, dgamma);
+        if (check_launch("ipa_ds2_kernel")) return 1;
+    } else {
+        ipa_ds_kernel<<<grid, 256, smem, st>>>(p, dcat, d_og, delta, dP, Tz, dS, dgamma);
+        if (check_launch("ipa_ds_kernel")) return 1;
+    }
     if (dq_pts == nullptr) return 0;       // the caller computes the point gradients as tensor-core contractions over dS
     const size_t smem2 = sizeof(float) * (size_t)(32 * PQ3 + 32 * (PQ3 + 1));
     ipa_pts_grad_kernel<<<grid, 256, smem2, st>>>(p, dS, dq_pts, dkv_pts, 0);

@@ -49,7 +49,7 @@ _SIGS = {
     "dfold_ipa_prob_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
     "dfold_ipa_pair_fwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pp",
     "dfold_ipa_fused_fwd": "pppppppp" + "ppl" + "ppl" + "iiiiiiii" + "ff" + "pp",
-    "dfold_ipa_ds_bwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "ppppp" + "pppp" + "p",
+    "dfold_ipa_ds_bwd": "plppplpppp" + "ppl" + "iiiiiiii" + "ff" + "pppppp" + "pppp" + "p",
     "dfold_gemm_bf16x3_batched": "ppllll" + "liill" + "ppllll" + "llil" + "pllilf" + "p",
     "dfold_gemm_wgrad_bf16x3_batched": "pplllll" + "pplllll" + "lll" + "ii" + "iiiil" + "pllf" + "p",
     "dfold_score_fwd": "ppppp" + "pidddd" + "ffpil" + "ppi" + "p",
@@ -928,10 +928,24 @@ class _IpaAttnTCFn(Function):
         dq_pts, dkv_pts = new(*q_pts.shape), new(*kv_pts.shape)
         args = _IpaAttnTCFn._v2args(logit0, q_pts, kv_pts, pair, quat, trans, mask, gamma, p_hi, p_lo, n8, F_, N_, H_, C_, Pq, Pv, Cp, dfold, inf, eps)
         pts_gemm = PQ3 <= 31 and os.environ.get("DFOLD_IPA_PTS_GEMM", "1") != "0"
-        _check(lib().dfold_ipa_ds_bwd(*args, _ptr(dcat), _ptr(d_og), _ptr(delta), _ptr(dP), _ptr(Tz), _ptr(dS), _ptr(dgamma),
+        # rows (f, h, i) of the value-point output gradient: operand of dV_pts below and of the value-point term of dP here
+        dg = d_og.reshape(F_, N_, H_, PV3).permute(0, 2, 1, 3).reshape(F_ * H_ * N_, PV3).contiguous()
+        dg_hi, dg_lo = _planes_rows(dg)
+        Tog = None
+        if Pq == 8 and os.environ.get("DFOLD_IPA_DS_V1", "0") != "1":
+            # d_og . v_pts on the tensor cores: Tog[(f,h,i), j] = sum_e dg[(f,h,i), e] v_pts[(f,h,j), e]
+            vp = kv_pts.reshape(F_, N_, H_, W)[..., PQ3:].permute(0, 2, 1, 3).reshape(F_ * H_ * N_, PV3).contiguous()
+            vp_hi, vp_lo = _planes_rows(vp)
+            Tog = new(F_ * H_ * N_, N_)
+            _check(lib().dfold_gemm_bf16x3_batched(
+                _ptr(dg_hi), _ptr(dg_lo), F_ * H_, N_, PV3, dg_hi.shape[1], F_ * H_, F_ * H_, 1, 0, PV3,
+                _ptr(vp_hi), _ptr(vp_lo), F_ * H_, N_, PV3, vp_hi.shape[1], 0, 0, 1, N_,
+                _ptr(Tog), N_, F_ * H_ * N_, 1, 0, 1.0, _stream()), "dfold_gemm_bf16x3_batched")
+        _check(lib().dfold_ipa_ds_bwd(*args, _ptr(dcat), _ptr(d_og), _ptr(delta), _ptr(dP), _ptr(Tz), _ptr(Tog), _ptr(dS), _ptr(dgamma),
                                       None if pts_gemm else _ptr(dq_pts), _ptr(dkv_pts), _stream()), "dfold_ipa_ds_bwd")
         del Tz
         del dP
+        del Tog
         if pts_gemm:
             # Point gradients as two small tensor-core contractions over dS instead of the CUDA-core / LDS-bound pass:
             #   dq_pts[i] = -gamma (q_i rowsum_i - sum_j dS_ij k_j),   dk_pts[j] = gamma (sum_i dS_ij q_i - colsum_j k_j)
@@ -973,8 +987,6 @@ class _IpaAttnTCFn(Function):
             C_, F_, N_, H_, splits, H_, 1, 1, 0, C_,
             _ptr(dkv, C_), H_ * 2 * C_, 2 * C_, 1.0, _stream()), "dfold_gemm_wgrad_bf16x3_batched")
         # ---- dV_pts[f,j,h,e] = sum_i P[f,h,i,j] d_og[f,i,h,e] ----
-        dg = d_og.reshape(F_, N_, H_, PV3).permute(0, 2, 1, 3).reshape(F_ * H_ * N_, PV3).contiguous()
-        dg_hi, dg_lo = _planes_rows(dg)
         tmp = new(F_ * H_, N_, PV3)
         _check(lib().dfold_gemm_wgrad_bf16x3_batched(
             _ptr(p_hi), _ptr(p_lo), N_, N_, F_ * H_, n8, N_ * n8,

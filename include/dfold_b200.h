@@ -202,12 +202,16 @@ int dfold_ipa_pre_bwd(const float* quat, const float* trans, int F, int N, int H
                       const float* out_cat, const float* dcat, float* d_og, float* delta, float* dquat, float* dtrans,
                       void* stream);
 /* dS = P (dP + d_og.v_pts + dO_pair.z - delta) [F,H,N,N], dgamma [H] (pre-zeroed), dq_pts, key part of dkv_pts.
- * Tz (nullable) = the dO_pair.z term precomputed as [N(i)][F*H][N(j)] by dfold_gemm_bf16x3_batched. */
+ * Tz (nullable) = the dO_pair.z term precomputed as [N(i)][F*H][N(j)] by dfold_gemm_bf16x3_batched.
+ * Tog (nullable; needs Tz and Pq = 8) = the value-point term d_og.v_pts precomputed as [F,H,N,N] the same way: the kernel then
+ * keeps each key's points in registers and only adds, scales and accumulates d(gamma).  dq_pts null: the caller computes
+ * the point gradients as contractions over dS. */
 int dfold_ipa_ds_bwd(const float* logit0, long logit0_fstride, const float* q_pts, const float* kv_pts, const float* pair,
                      long pair_fstride, const float* quat, const float* trans, const float* mask, const float* gamma,
                      uint16_t* p_hi, uint16_t* p_lo, long ldp, int F, int N, int H, int C, int Pq, int Pv, int Cp,
                      int dfold, float inf, float eps, const float* dcat, const float* d_og, const float* delta,
-                     const float* dP, const float* Tz, float* dS, float* dgamma, float* dq_pts, float* dkv_pts, void* stream);
+                     const float* dP, const float* Tz, const float* Tog, float* dS, float* dgamma, float* dq_pts,
+                     float* dkv_pts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Score epilogue (csrc/epilogue.cu), one warp per residue, no [n,L] temporaries, no host synchronisation.

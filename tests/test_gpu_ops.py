@@ -193,9 +193,9 @@ def test_ipa_attention(F, N, H, C, Pq, Pv, Cp, Fs, Fz, dfold, masked):
     # quantises the logits to 2^-7, so those rows are compared only through the unmasked ones
     post = lambda out, *a: out * a[7][:, :, None]
     # d(gamma) [H] (gradient 7: the mask carries none) is a signed sum over all F*N*N pairs of a head whose terms are orders
-    # of magnitude larger than the sum; the fp32 rounding of the logits alone moves it by ~2e-4 relative, run to run with
-    # the atomic accumulation order
-    check("ipa_attention", inputs, 2e-4, post=post, grad_tol={7: 6e-4}, Pq=Pq, Pv=Pv, dfold=dfold, inf=1e5, eps=1e-8)
+    # of magnitude larger than the sum: the fp32 rounding of the logits alone moves it by ~2e-4 relative, run to run with the
+    # atomic accumulation order, and the split-bf16 value-point term of dS (2^-17 per product) by up to ~7e-4
+    check("ipa_attention", inputs, 2e-4, post=post, grad_tol={7: 1.5e-3}, Pq=Pq, Pv=Pv, dfold=dfold, inf=1e5, eps=1e-8)
 
 
 @pytest.mark.parametrize("F,N,Ci,Co,crop", [(7, 24, 64, 128, 2), (17, 40, 160, 80, 2), (5, 130, 128, 64, 4)])
