@@ -557,13 +557,15 @@ __global__ void adam_tick_kernel(float* step) { *step += 1.f; }
 
 __global__ void __launch_bounds__(256) adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                            float* __restrict__ v, float* __restrict__ vmax, long n4,
-                                                           const float* __restrict__ step, float lr, float b1, float b2, float eps) {
+                                                           const float* __restrict__ step, float lr, float b1, float b2, float eps,
+                                                           float gscale) {
     const float t = *step;
     const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     const float step_size = lr / bc1, inv_bc2_sqrt = 1.f / sqrtf(bc2);
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 P = reinterpret_cast<float4*>(p)[i];
-        const float4 G = reinterpret_cast<const float4*>(g)[i];
+        float4 G = reinterpret_cast<const float4*>(g)[i];
+        G.x *= gscale; G.y *= gscale; G.z *= gscale; G.w *= gscale;      // 1 / world_size of the data-parallel mean
         float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i], X = reinterpret_cast<float4*>(vmax)[i];
         float* pp = &P.x; const float* gg = &G.x; float* mm = &M.x; float* vv = &V.x; float* xx = &X.x;
 #pragma unroll
@@ -584,12 +586,12 @@ __global__ void __launch_bounds__(256) adam_amsgrad_kernel(float* __restrict__ p
 
 // n must be a multiple of 4 and the buffers 16-byte aligned (train_step.py pads its flat buffers).
 extern "C" int dfold_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
-                                  float* step, float lr, float beta1, float beta2, float eps, void* stream) {
+                                  float* step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
     DFOLD_REQUIRE(n > 0 && n % 4 == 0, "dfold_adam_amsgrad: n must be a positive multiple of 4");
     cudaStream_t st = dfold::as_stream(stream);
     dfold::adam_tick_kernel<<<1, 1, 0, st>>>(step);
     const long n4 = n / 4;
     const int blocks = (int)(dfold::cdiv(n4, 256) < 148 * 16 ? dfold::cdiv(n4, 256) : 148 * 16);
-    dfold::adam_amsgrad_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n4, step, lr, beta1, beta2, eps);
+    dfold::adam_amsgrad_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n4, step, lr, beta1, beta2, eps, grad_scale);
     return dfold::check_launch("adam_amsgrad_kernel");
 }

@@ -128,7 +128,8 @@ class TrainStep:
         loss.backward()
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
-            self.flat_grad.mul_(1.0 / self.world)
+            if self.opt is not None:
+                self.flat_grad.mul_(1.0 / self.world)       # (the fused optimizer scales the summed gradient on the fly)
         self.optimizer_step()
         self.loss.copy_(loss.detach().float())
 
@@ -139,7 +140,7 @@ class TrainStep:
         K = _kernels
         K._check(K.lib().dfold_adam_amsgrad(K._ptr(self.flat_param), K._ptr(self.flat_grad), K._ptr(self.exp_avg),
                                             K._ptr(self.exp_avg_sq), K._ptr(self.max_exp_avg_sq), self.flat_param.numel(),
-                                            K._ptr(self.step_count), self.lr, 0.9, 0.999, 1e-8, K._stream()), "dfold_adam_amsgrad")
+                                            K._ptr(self.step_count), self.lr, 0.9, 0.999, 1e-8, 1.0 / self.world, K._stream()), "dfold_adam_amsgrad")
         K.invalidate_weight_cache()                    # the weights moved without touching their version counters
 
     def load(self, feats: Dict[str, torch.Tensor]):
