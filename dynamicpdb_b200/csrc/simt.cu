@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) conv_weight_prep_kernel(const float* __re
 }
 
 // g[T][O][I] -> out[O][I][T]   (weight-gradient layout back to the parameter's [C_out, C_in, 5, 5])
-__global__ void taps_to_param_kernel(const float* __restrict__ g, int O, int I, int T, float* __restrict__ out) {
+__global__ void taps_to_param_kernel(const float* __restrict__ g, int O, int I, int T, float* __restrict__ out, int accumulate) {
     extern __shared__ float smf[];                    // [T][65]
     const int o = blockIdx.y;
     const int i0 = blockIdx.x * 64;
@@ -199,7 +199,7 @@ __global__ void taps_to_param_kernel(const float* __restrict__ g, int O, int I, 
     float* dst = out + ((long)o * I + i0) * T;
     for (int e = threadIdx.x; e < ni * T; e += blockDim.x) {
         const int ii = e / T, t = e % T;
-        dst[e] = smf[t * 65 + ii];
+        dst[e] = (accumulate ? dst[e] : 0.f) + smf[t * 65 + ii];
     }
 }
 
@@ -485,10 +485,10 @@ extern "C" int dfold_conv_weight_prep(const float* w, int O, int I, int T, uint1
     return check_launch("conv_weight_prep_kernel");
 }
 
-extern "C" int dfold_taps_to_param(const float* g, int O, int I, int T, float* out, void* stream) {
+extern "C" int dfold_taps_to_param(const float* g, int O, int I, int T, float* out, int accumulate, void* stream) {
     DFOLD_REQUIRE(O > 0 && I > 0 && T > 0 && T <= 64, "dfold_taps_to_param: bad shape");
     dim3 grid((unsigned)cdiv(I, 64), (unsigned)O);
-    taps_to_param_kernel<<<grid, 256, T * 65 * sizeof(float), as_stream(stream)>>>(g, O, I, T, out);
+    taps_to_param_kernel<<<grid, 256, T * 65 * sizeof(float), as_stream(stream)>>>(g, O, I, T, out, accumulate);
     return check_launch("taps_to_param_kernel");
 }
 

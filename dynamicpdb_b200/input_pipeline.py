@@ -119,6 +119,23 @@ class WindowPrefetcher:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.store, self.rows, self.device, self.training, self.depth = store, list(rows), dev, training, depth
         self.stream = torch.cuda.Stream(device=self.device)
+        self._staging: Dict = {}
+        self._slot: Dict[str, int] = {}
+
+    def _stage(self, name: str, src: torch.Tensor, sl: slice) -> torch.Tensor:
+        """The (possibly strided) frame window gathered into a pinned staging buffer: a ring of depth + 1 buffers per field,
+        so a buffer is reused only after the consumer has received the window that was copied from it."""
+        n = len(range(*sl.indices(src.shape[0])))
+        shape = (n,) + tuple(src.shape[1:])
+        ring = self._staging.setdefault((name, shape, src.dtype), [])
+        if len(ring) <= self.depth:
+            buf = torch.empty(shape, dtype=src.dtype)
+            ring.append(buf.pin_memory() if self.store.pin else buf)
+        slot = self._slot.get(name, 0)
+        self._slot[name] = (slot + 1) % (self.depth + 1)
+        buf = ring[min(slot, len(ring) - 1)]
+        buf.copy_(src[sl])
+        return buf
 
     def _make(self, row) -> Tuple[Dict[str, torch.Tensor], torch.cuda.Event]:
         ent = self.store.protein(*row)
@@ -126,13 +143,13 @@ class WindowPrefetcher:
         nf = self.store.frame_time
         with torch.cuda.stream(self.stream):
             cp = lambda t: t.to(self.device, non_blocking=True)
-            atom37 = cp(ent["atom37"][sl].contiguous().pin_memory() if self.store.pin else ent["atom37"][sl].contiguous())
+            atom37 = cp(self._stage("atom37", ent["atom37"], sl))
             feats = featurize_window(atom37, cp(ent["atom_mask"]), cp(ent["aatype"]))
             feats.update({
                 "aatype": cp(ent["aatype"]).unsqueeze(0).expand(nf, -1),
                 "seq_idx": cp(ent["residue_index"]).unsqueeze(0).expand(nf, -1),
                 "residue_index": cp(ent["residue_index"]).unsqueeze(0).expand(nf, -1),
-                "force": cp(ent["force"][sl].contiguous()), "vel": cp(ent["vel"][sl].contiguous()),
+                "force": cp(self._stage("force", ent["force"], sl)), "vel": cp(self._stage("vel", ent["vel"], sl)),
                 "node_repr": cp(ent["node_repr"]), "edge_repr": cp(ent["edge_repr"]),
                 "fixed_mask": torch.zeros(nf, atom37.shape[1], dtype=torch.float64, device=self.device),
                 "sc_ca_t": torch.zeros(nf, atom37.shape[1], 3, dtype=torch.float32, device=self.device),

@@ -29,7 +29,7 @@ _SIGS = {
     "dfold_debug_ipa_stats": "p",
     "dfold_split2d": "plllipl" + "ppll" + "ppll" + "pp",
     "dfold_conv_weight_prep": "piii" + "ppl" + "ppl" + "p",
-    "dfold_taps_to_param": "piiipp",
+    "dfold_taps_to_param": "piiipip",
     "dfold_sgemm": "pllll" * 4 + "p" + "iiiii" + "ff" + "iii" + "p",
     "dfold_global_layernorm_fwd": "pppplfip",
     "dfold_global_layernorm_bwd": "pppppl" + "ip",
@@ -94,6 +94,10 @@ def exported_symbols():
 _LAUNCHES_PER_CALL = {"dfold_global_layernorm_fwd": 3, "dfold_global_layernorm_bwd": 3, "dfold_ipa_attn_bwd": 4,
                       "dfold_ipa_ds_bwd": 3}
 LAUNCH_COUNT = 0
+# When True (set by train_step.TrainStep around its step), weight gradients of the convolution are accumulated by the kernel
+# straight into the parameter's existing .grad buffer and autograd receives None: the ConvNet is shared by the four blocks
+# (ipa_pytorch_dynamic.py:749,863), so the default path costs three 82 MB add passes per weight and step.
+GRAD_ACCUMULATE_INPLACE = False
 # optional per-launch timing: when PROFILE is a list, timed(...) appends (name, work, start_event, end_event)
 PROFILE = None
 
@@ -423,6 +427,7 @@ class _Conv5x5Fn(Function):
               r2, Co, 1.0, 1.0, 1 if relu else 0, F_out=Fo, f_start=crop)
         ctx.save_for_backward(a_hi, a_lo, w, out if relu else None, r2 if relu else None)
         ctx.meta = (x.shape, relu, b is not None, residual is not None, crop)
+        ctx.w_param = w if isinstance(w, torch.nn.Parameter) else None
         return out.reshape(Fo, N_, Co)
 
     @staticmethod
@@ -450,8 +455,13 @@ class _Conv5x5Fn(Function):
         if need_w:
             taps = torch.empty((kh * kw, Co, Ci), dtype=torch.float32, device=g.device)
             _gemm_wgrad((g_hi, g_lo), Co, Co, (x_hi, x_lo), Ci, Ci, Fo, N_, kh, kw, taps, Ci, Fb=F_, b_f_add=crop)
-            dw = torch.empty((Co, Ci, kh, kw), dtype=torch.float32, device=g.device)
-            _check(lib().dfold_taps_to_param(_ptr(taps), Co, Ci, kh * kw, _ptr(dw), _stream()), "dfold_taps_to_param")
+            wp = ctx.w_param
+            acc = wp.grad if (GRAD_ACCUMULATE_INPLACE and wp is not None) else None
+            if acc is not None and acc.dtype == torch.float32 and acc.is_contiguous() and acc.shape == w.shape and acc.device == g.device:
+                _check(lib().dfold_taps_to_param(_ptr(taps), Co, Ci, kh * kw, _ptr(acc), 1, _stream()), "dfold_taps_to_param")
+            else:
+                dw = torch.empty((Co, Ci, kh, kw), dtype=torch.float32, device=g.device)
+                _check(lib().dfold_taps_to_param(_ptr(taps), Co, Ci, kh * kw, _ptr(dw), 0, _stream()), "dfold_taps_to_param")
         return dx, dw, db, None, (dy if has_r else None), None
 
 

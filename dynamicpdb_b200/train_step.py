@@ -125,7 +125,11 @@ class TrainStep:
         self.flat_grad.zero_()
         out = self.net(dict(self.static))
         loss = self.loss_fn(out)
-        loss.backward()
+        prev, _kernels.GRAD_ACCUMULATE_INPLACE = _kernels.GRAD_ACCUMULATE_INPLACE, True     # wgrad kernels add into the flat buffer
+        try:
+            loss.backward()
+        finally:
+            _kernels.GRAD_ACCUMULATE_INPLACE = prev
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
             if self.opt is not None:

@@ -51,8 +51,9 @@ int dfold_split2d(const float* x, long R, long C, long ld, int pre_relu, const f
 int dfold_conv_weight_prep(const float* w, int O, int I, int T, uint16_t* f_hi, uint16_t* f_lo, long ldi,
                            uint16_t* d_hi, uint16_t* d_lo, long ldo, void* stream);
 
-/* g[T][O][I] -> out[O][I][T]: weight gradient back to the parameter layout. */
-int dfold_taps_to_param(const float* g, int O, int I, int T, float* out, void* stream);
+/* g[T][O][I] -> out[O][I][T]: weight gradient back to the parameter layout; accumulate != 0 adds into `out` (the shared
+ * ConvNet's four weight gradients of a step land in the gradient buffer without separate add passes). */
+int dfold_taps_to_param(const float* g, int O, int I, int T, float* out, int accumulate, void* stream);
 
 /* for f in [0, F_out):
  * out[f*Nr + n, c] = act(alpha * sum_{tf,tn,k} A[f + f_start + tf - taps_f/2, n + tn - taps_n/2, k] * B[tf*taps_n+tn][c][k]

@@ -86,3 +86,23 @@ def test_fused_adam_matches_torch_adam_amsgrad():
                                             1e-3, 0.9, 0.999, 1e-8, 1.0, K._stream()), "dfold_adam_amsgrad")
         assert (p - ref.detach()).abs().max().item() < 2e-6 * max(1.0, ref.abs().max().item()), it
     assert torch.equal(p[:100], p0[:100]) and float(step) == 6.0
+
+
+def test_train_step_gradients_equal_plain_autograd(monkeypatch):
+    """The step accumulates the shared ConvNet's weight gradients in place (kernels.GRAD_ACCUMULATE_INPLACE) and updates flat
+    parameter views: its gradient buffer must equal what loss.backward() gives on an untouched copy of the network."""
+    monkeypatch.setenv("DFOLD_GEMM_NO_SPLITK", "1")
+    nf, N = 3, 24
+    feats = {k: v.cuda() for k, v in syn.make_feats(nf, N, seed=4).items()}
+    base = _net(nf, syn.PRESET_TINY)
+    ref = copy.deepcopy(base)
+    syn.surrogate_loss(ref(dict(feats))).backward()
+    ts = TrainStep(base, syn.surrogate_loss, feats, lr=1e-3, graph=False, warmup=1)
+    ts()
+    off = 0
+    for (name, p), q in zip(base.named_parameters(), ref.parameters()):
+        n = p.numel()
+        g = ts.flat_grad[off:off + n].view_as(p)
+        off += n
+        want = torch.zeros_like(g) if q.grad is None else q.grad
+        assert (g - want).abs().max().item() <= 2e-5 * max(1e-6, want.abs().max().item()) + 1e-9, name
