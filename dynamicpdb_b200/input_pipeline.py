@@ -121,6 +121,7 @@ class WindowPrefetcher:
         self.stream = torch.cuda.Stream(device=self.device)
         self._staging: Dict = {}
         self._slot: Dict[str, int] = {}
+        self._events: list = []
 
     def _stage(self, name: str, src: torch.Tensor, sl: slice) -> torch.Tensor:
         """The (possibly strided) frame window gathered into a pinned staging buffer: a ring of depth + 1 buffers per field,
@@ -139,6 +140,9 @@ class WindowPrefetcher:
 
     def _make(self, row) -> Tuple[Dict[str, torch.Tensor], torch.cuda.Event]:
         ent = self.store.protein(*row)
+        # the staging buffers of this window were last used depth + 1 windows ago: that copy must have left the host
+        if len(self._events) > self.depth:
+            self._events[-(self.depth + 1)].synchronize()
         sl = self.store.window_index(ent["atom37"].shape[0], self.training)
         nf = self.store.frame_time
         with torch.cuda.stream(self.stream):
@@ -156,6 +160,8 @@ class WindowPrefetcher:
             })
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self._events.append(ev)
+        del self._events[:-(self.depth + 2)]
         return feats, ev
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
