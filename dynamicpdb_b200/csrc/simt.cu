@@ -586,10 +586,10 @@ __global__ void __launch_bounds__(256) adam_amsgrad_kernel(float* __restrict__ p
 
 // n must be a multiple of 4 and the buffers 16-byte aligned (train_step.py pads its flat buffers).
 extern "C" int dfold_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
-                                  float* step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                                  float* step, int tick, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream) {
     DFOLD_REQUIRE(n > 0 && n % 4 == 0, "dfold_adam_amsgrad: n must be a positive multiple of 4");
     cudaStream_t st = dfold::as_stream(stream);
-    dfold::adam_tick_kernel<<<1, 1, 0, st>>>(step);
+    if (tick) dfold::adam_tick_kernel<<<1, 1, 0, st>>>(step);      // chunked callers advance the step once per optimizer step
     const long n4 = n / 4;
     const int blocks = (int)(dfold::cdiv(n4, 256) < 148 * 16 ? dfold::cdiv(n4, 256) : 148 * 16);
     dfold::adam_amsgrad_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n4, step, lr, beta1, beta2, eps, grad_scale);

@@ -56,7 +56,7 @@ _SIGS = {
     "dfold_score_bwd": "ppppp" + "pidddd" + "ffpil" + "ppi" + "pp" + "p",
     "dfold_frames_to_atoms_fwd": "pippp" + "pppppp" + "ppp" + "lp",
     "dfold_reverse_step": "ppppi" + "ppp" + "dddddd" + "iii" + "pp" + "llp",
-    "dfold_adam_amsgrad": "pppppl" + "p" + "fffff" + "p",
+    "dfold_adam_amsgrad": "pppppl" + "pi" + "fffff" + "p",
     "dfold_featurize_window": "pppppp" + "ii" + "pppp" + "p",
     "dfold_loss_fwd": "pppppppppppp" + "ii" + "dddd" + "ii" + "pppp" + "p",
     "dfold_quat_mul_fwd": "ppplip",

@@ -296,10 +296,11 @@ int dfold_featurize_window(const float* pos, const float* atom_mask, const long*
                            double* tmask, void* stream);
 
 /* Adam (amsgrad) of the reference trainer (torch.optim.Adam(amsgrad=True), train_DFOLD_dynamics.py:412) in one pass over
- * flat fp32 buffers of n elements (n % 4 == 0); `step` is a device float incremented by the call (graph capturable);
+ * flat fp32 buffers of n elements (n % 4 == 0); `step` is a device float, incremented by the call when tick != 0 (graph
+ * capturable; a caller that updates the buffers chunk by chunk ticks once per optimizer step);
  * the gradient is multiplied by grad_scale on the fly (1 / world_size after a summing all-reduce). */
 int dfold_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, long n,
-                       float* step, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+                       float* step, int tick, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
