@@ -182,6 +182,8 @@ def _ipa_inputs(F, N, H, C, Pq, Pv, Cp, Fs, Fz, masked):
     (2, 20, 12, 16, 4, 8, 32, 1, 1, True),     # preset B
     (2, 40, 8, 256, 8, 12, 32, 1, 1, True),    # preset A geometry (tensor-core decomposition)
     (3, 256, 8, 256, 8, 12, 32, 1, 1, True),   # preset A, N = 256
+    (1, 32, 8, 256, 8, 12, 32, 1, 1, True),    # fused kernel, exactly one key tile
+    (2, 24, 8, 256, 8, 12, 32, 1, 1, True),    # fused kernel, one partial key tile
     (2, 136, 4, 64, 4, 6, 16, 1, 1, False),    # tensor-core path, vanilla layout, N not a multiple of 64
     (2, 33, 4, 16, 4, 8, 64, 2, 2, False),     # vanilla OpenFold, batched z and per-frame s
     (3, 70, 2, 8, 2, 3, 4, 3, 1, True),        # per-frame s, shared z, N not a multiple of the tiles
