@@ -139,6 +139,16 @@ def test_ops_refuse_cpu_tensors():
         kernels.global_layernorm(torch.zeros(2, 3, 4))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         kernels.conv5x5(torch.zeros(2, 8, 8), torch.zeros(8, 8, 5, 5))
+    # the widened rows (loss, input featurisation) have no host path either
+    from dynamicpdb_b200 import synthetic as syn
+    from dynamicpdb_b200.input_pipeline import featurize_window
+    from dynamicpdb_b200.loss import score_network_loss
+    from oracle import dfold_oracle as O
+    feats, out, _ = syn.loss_variant("plain")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        score_network_loss(out, feats, O.default_exp_conf())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        featurize_window(torch.zeros(2, 5, 37, 3), torch.ones(5, 37), torch.zeros(5, dtype=torch.long))
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference checkout not mounted")
