@@ -4,13 +4,14 @@
 // tensor-core variant).  Per CTA, over key tiles of 32 residues:
 //   pass 1   exact softmax statistics (row max m, row sum l) of
 //                s[h,i,j] = logit0[h,i,j] - gamma_h/2 * sum_p |q_p(i) - k_p(j)|^2 + inf * (mask_i mask_j - 1)
-//            with the coordinate differences in exact fp32 (packed FADD2 / FFMA2), per-lane online (m, l) in registers
-//            and one warp-shuffle combine per row at the end -- no whole-row shared memory, no cap on N;
+//            with the coordinate differences in exact fp32 (packed FADD2 / FFMA2): key points arrive by TMA (double-buffered
+//            tiles), each lane keeps one key in registers, the query points are broadcast from shared memory, (m, l) are
+//            kept online per lane and combined by warp shuffles at the end -- no whole-row shared memory, no cap on N;
 //   pass 2   per key tile: (A) p = exp(s - m) / l, written once to shared memory (fp32, all heads), to the bf16
 //            hi/lo planes P[F,H,N,ldp] that the backward GEMMs read, and (tensor-core variant) to a 128B-swizzled
 //            bf16 hi/lo operand tile; (B1) pair aggregation o_pair[i,h,:] += p[h,i,j] z[i,j,:] with lanes across the
 //            pair channels, z read once from L2 for all 8 heads; (B2) value-point aggregation
-//            o_pt[h,i,:] += p[h,i,j] v_pts[j,h,:] with the value points staged by cp.async;
+//            o_pt[h,i,:] += p[h,i,j] v_pts[j,h,:] with the tile's value points landing as one TMA box;
 //   P V      tensor-core variant: the control warp streams V^T tiles (MN-major, straight from the [N, H*2C] bf16 planes
 //            of kv) through a TMA / mbarrier ring and issues tcgen05.mma  O^T[c, i] += V^T[c, j] P^T[j, i]  (M = 128 c,
 //            N = 32 rows, hi*hi + hi*lo + lo*hi) into 16 TMEM accumulators (8 heads x 2 halves of C = 256) = all 512
