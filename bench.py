@@ -324,9 +324,24 @@ def extra_configs(dev, graph):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / reps
             res[name] = {"ms_per_sample": ms, "frames_per_s": nf / (ms * 1e-3), "denoise_steps_per_s": num_t / (ms * 1e-3)}
+        try:
+            sampler.memo.reset()
+            sampler.sample_graphed(feats, num_t, 0.01)              # capture (trunk + 100 steps in one CUDA graph)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                sampler.sample_graphed(feats, num_t, 0.01)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            res["memoised_graph"] = {"ms_per_sample": ms, "frames_per_s": nf / (ms * 1e-3), "denoise_steps_per_s": num_t / (ms * 1e-3)}
+        except Exception as e:      # noqa: BLE001
+            res["memoised_graph"] = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
         out["inference_100step"] = {
             "workload": "configs[1]: 100-step reverse diffusion, N_res=256, 32 frames, 1 GPU", **res,
-            "note": "memoised = one trunk pass + 100 x (score-epilogue kernel + reverse-step kernel) on the device; literal = the "
+            "note": "memoised = one trunk pass + 100 x (score-epilogue kernel + reverse-step kernel) on the device; memoised_graph = the "
+                    "same work replayed from one CUDA graph (input copies included); literal = the "
                     "reference's schedule (whole network at every step) with the device reverse step"}
         del net, sampler, feats
         torch.cuda.empty_cache()

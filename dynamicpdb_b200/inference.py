@@ -78,6 +78,48 @@ class DeviceReverseDiffusion:
         if not isinstance(sd, SE3ScoreDiffuser):
             raise ValueError("DeviceReverseDiffusion needs a diffuser with the reference's logarithmic / VP-SDE schedules")
         self.diffuser = sd
+        self._graphs: Dict = {}
+
+    @torch.no_grad()
+    def sample_graphed(self, data_init: Dict[str, torch.Tensor], num_t: int, min_t: float, noise_scale: float = 1.0,
+                       center: bool = True, noise=None):
+        """``sample`` (memoised) replayed from ONE CUDA graph holding the trunk pass and all ``num_t`` score / reverse steps:
+        the per-step work is two small kernels plus a few tensor views, so launched eagerly the loop is bound by Python and
+        launch latency, not by the device.  The graph is captured on the first call for a given (schedule, shapes) and reads
+        its inputs from static buffers; without injected ``noise`` the normal draws come from the default CUDA generator
+        (graph-aware: every replay draws fresh numbers)."""
+        key = (num_t, float(min_t), float(noise_scale), bool(center), noise is not None,
+               tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(data_init.items())))
+        ent = self._graphs.get(key)
+        if ent is None:
+            static = {k: v.clone() for k, v in data_init.items()}
+            static_noise = None if noise is None else (noise[0].clone(), noise[1].clone())
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                     # warm-up: allocator pools, library load, plane caches
+                self.memo.reset()
+                self.sample(static, num_t, min_t, noise_scale, center, static_noise)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            self.memo.reset()                                 # the trunk pass must be part of the captured work
+            from . import kernels as K
+            K.invalidate_weight_cache()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = self.sample(static, num_t, min_t, noise_scale, center, static_noise)
+            self.memo.reset()                                 # its cache now points into the graph's private pool
+            K.invalidate_weight_cache()
+            ent = (g, static, static_noise, res)
+            self._graphs[key] = ent
+        g, static, static_noise, res = ent
+        for k, v in data_init.items():
+            static[k].copy_(v)
+        if noise is not None:
+            static_noise[0].copy_(noise[0])
+            static_noise[1].copy_(noise[1])
+        g.replay()
+        return {k: v.clone() for k, v in res.items()}
 
     @torch.no_grad()
     def sample(self, data_init: Dict[str, torch.Tensor], num_t: int, min_t: float, noise_scale: float = 1.0, center: bool = True,

@@ -63,6 +63,27 @@ def test_device_sampler_matches_literal_loop(monkeypatch):
     assert float((a["rigids"][:, 0, 4:] - feats["rigids_t"][:, 0, 4:]).abs().max()) > 0     # last step returns the prediction
 
 
+def test_graphed_sampler_replays_match_eager(monkeypatch):
+    """The trunk pass + every score / reverse step captured in one CUDA graph: replays with new inputs reproduce the eager
+    loop (injected noise, deterministic GEMM schedule)."""
+    monkeypatch.setenv("DFOLD_GEMM_NO_SPLITK", "1")
+    nf, N, num_t = 3, 24, 6
+    net = _net(nf, syn.PRESET_TINY)
+    g = torch.Generator().manual_seed(2)
+    noise = (torch.randn(num_t, nf, N, 3, generator=g).to(DEV), torch.randn(num_t, nf, N, 3, generator=g).to(DEV))
+    s = DeviceReverseDiffusion(net)
+    for seed in (6, 7):                                      # second window: a pure replay from the static buffers
+        feats = {k: v.to(DEV) for k, v in syn.make_feats(nf, N, seed=seed).items()}
+        a = s.sample_graphed(feats, num_t, 0.01, noise_scale=0.5, noise=noise)
+        s.memo.reset()
+        b = s.sample(feats, num_t, 0.01, noise_scale=0.5, noise=noise)
+        for k in b:
+            assert a[k].shape == b[k].shape and close(a[k].cpu(), b[k].cpu(), 1e-6), (seed, k)
+    assert len(s._graphs) == 1
+    c = s.sample_graphed(feats, num_t, 0.01, noise_scale=0.5)    # device-generated noise: its own graph, finite output
+    assert len(s._graphs) == 2 and bool(torch.isfinite(c["rigids"]).all())
+
+
 def test_memoized_network_on_gpu_and_cache_invalidation(monkeypatch):
     """MemoizedScoreNetwork on CUDA: a new window allocated at the same address must NOT hit the cache."""
     monkeypatch.setenv("DFOLD_GEMM_NO_SPLITK", "1")       # two evaluations are compared at 1e-6: deterministic schedule
