@@ -77,12 +77,14 @@ class TrajectoryStore:
         """Load (once) and cache one protein: the file naming follows Dfold_data_loader_dynamic.py:194-198."""
         if atlas_npz in self._cache:
             return self._cache[atlas_npz]
-        z = np.load(atlas_npz, allow_pickle=True)
+        with np.load(atlas_npz, allow_pickle=True) as zf:
+            z = {k: zf[k] for k in ("all_atom_positions", "all_atom_mask", "aatype", "residue_index")}
         with open(force_path.replace(".pkl", "_Ca.pkl"), "rb") as f:
             force = pickle.load(f)
         with open(vel_path.replace(".pkl", "_ca.pkl"), "rb") as f:
             vel = pickle.load(f)
-        emb = np.load(embed_path)
+        with np.load(embed_path) as ef:
+            emb = {k: ef[k] for k in ("node_repr", "edge_repr")}
         kf = self.keep_first
         ent = {
             "atom37": self._pin(z["all_atom_positions"][:kf], torch.float32),                 # [T,N,37,3]
