@@ -94,3 +94,31 @@ def test_two_pass_tiled_softmax_and_split_product_match_the_oracle():
     assert rel(o, ref_o, keep[..., None]) < 2e-5                             # split-bf16 product, fp32 accumulate
     assert rel(o_pair, ref_pair, keep[..., None]) < 2e-5
     assert rel(o_pt, ref_pt, keep[..., None, None]) < 2e-5
+
+
+def test_point_gradients_as_contractions_with_a_ones_column():
+    """The backward computes dq_pts / dk_pts as two contractions over dS with a ones column appended to the point operands
+    (kernels._IpaAttnTCFn.backward): the row / column sums of dS fall out of the same products.  Checked against the direct
+    sum over coordinate differences (csrc/ipa_v2.cu ipa_pts_grad_kernel), with the split-bf16 product error included."""
+    torch.manual_seed(1)
+    N, PQ3, gam = 96, 24, 0.17
+    q, k = torch.randn(N, PQ3) * 6 + 20.0, torch.randn(N, PQ3) * 6 + 20.0     # coordinates far from the origin: cancellation
+    P = torch.softmax(torch.randn(N, N) * 2, dim=-1)
+    dP = torch.randn(N, N)
+    dS = P * (dP - (P * dP).sum(-1, keepdim=True))                             # softmax gradient: rows sum to ~0
+    diff = q[:, None, :].double() - k[None, :, :].double()
+    dq_ref = -gam * (dS.double()[:, :, None] * diff).sum(1)
+    dk_ref = gam * (dS.double()[:, :, None] * diff).sum(0)
+    ones = torch.ones(N, 1)
+    kt, qn = torch.cat([k, ones], dim=1), torch.cat([q, ones], dim=1)
+    s_hi, s_lo = split(dS)
+
+    def mm3(a_hi, a_lo, b):                                                    # hi*hi + hi*lo + lo*hi in fp32
+        b_hi, b_lo = split(b)
+        return a_lo @ b_hi + a_hi @ b_lo + a_hi @ b_hi
+    g1 = mm3(s_hi, s_lo, kt)                                                   # [i, 25]: sum_j dS k | rowsum
+    g2 = mm3(s_hi.T.contiguous(), s_lo.T.contiguous(), qn)                     # [j, 25]: sum_i dS q | colsum
+    dq = -gam * (q * g1[:, PQ3:] - g1[:, :PQ3])
+    dk = gam * (g2[:, :PQ3] - g2[:, PQ3:] * k)
+    rel = lambda a, b: (a.double() - b).abs().max().item() / b.abs().max().item()
+    assert rel(dq, dq_ref) < 2e-4 and rel(dk, dk_ref) < 2e-4                   # the op-level GPU tolerance
